@@ -1,0 +1,159 @@
+/*
+ * maray_cuda.h -- C ABI of the B200 (sm_100a) render path for Maray scenes.
+ *
+ * The reference (advancedresearch/maray v0.3.8, Rust) has no FFI: its render back ends are Rust
+ * functions behind `gen_to_image` (reference src/lib.rs:1177-1195).  This ABI is what a new
+ * `RenderMethod::Cuda` arm / `render::cuda_gen_to_image` would bind through `extern "C"`; each
+ * entry point names the reference interface it stands in for.  INTEGRATION.md shows the Rust side.
+ *
+ * Conventions
+ *   - every function returns MARAY_OK (0) or a negative MARAY_E_* code; the message for the last
+ *     failure on a handle is maray_cuda_last_error(h) (for a failed create: last_error(NULL));
+ *   - no exception or panic crosses this boundary; invalid scenes are rejected at load/compile
+ *     time, never by a device fault;
+ *   - the caller owns every host buffer it passes; the library copies what it keeps;
+ *   - a handle may be used from one thread at a time; calls block until their work is complete
+ *     unless they take a stream;
+ *   - there is NO CPU fallback: render calls fail with MARAY_E_CUDA when no usable GPU exists.
+ */
+#ifndef MARAY_CUDA_H
+#define MARAY_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct maray_cuda maray_cuda_t;
+
+enum {
+    MARAY_OK = 0,
+    MARAY_E_INVALID = -1,      /* bad argument / call order                                   */
+    MARAY_E_PARSE = -2,        /* not a .maray file (either layout)                           */
+    MARAY_E_SCENE = -3,        /* scene rejected: unbound variable, cyclic Let, App id out of the
+                                  texture runtime's table (the reference yields NaN / panics)   */
+    MARAY_E_COMPILE = -4,      /* NVRTC / code generation failure                             */
+    MARAY_E_CUDA = -5,         /* CUDA runtime failure or no usable device                    */
+    MARAY_E_UNSUPPORTED = -6   /* e.g. a Runtime other than the default texture runtime       */
+};
+
+/* Back ends (siblings of the reference's WAT code generator, reference src/wasm.rs). */
+enum {
+    MARAY_BACKEND_INTERP = 0,  /* flat register bytecode run by the hand-written interpreter kernel */
+    MARAY_BACKEND_NVRTC = 1    /* straight-line CUDA compiled at run time for sm_100a, --fmad=false  */
+};
+
+/* Progress reporting, the counterpart of `Report` (reference src/report.rs:19-27).  The callback is
+ * the counterpart of the `report: F` closure of gen_to_image (reference src/lib.rs:1183):
+ * it receives the caller's image buffer with the rows finished so far filled in, and progress in
+ * [0,1].  It is invoked on the calling thread, between row bands. */
+enum { MARAY_REPORT_NONE = 0, MARAY_REPORT_ROW = 1, MARAY_REPORT_DURATION_MS = 2 };
+typedef void (*maray_report_fn)(void* user, uint8_t* rgb, uint32_t w, uint32_t h, double progress);
+
+/* What the lowering found and what the last compile/render cost. */
+typedef struct maray_cuda_stats {
+    /* program */
+    uint64_t tree_nodes;          /* nodes of the three channel trees as stored on the wire          */
+    uint64_t dag_nodes;           /* values after hash-consing across the channels                   */
+    uint64_t n_const, n_x_only, n_y_only, n_xy;
+    uint64_t n_add, n_mul, n_neg, n_abs, n_recip, n_sqrt, n_step, n_min, n_max, n_sin, n_exp, n_ln, n_tex;
+    uint32_t dag_depth;
+    uint32_t legacy_layout;       /* 1 when the file used the pre-`Arc` variant numbering            */
+    /* back end */
+    uint32_t backend;
+    uint32_t interp_instructions; /* bytecode length (interpreter back end)                          */
+    uint32_t interp_slots;        /* per-pixel value slots the bytecode needs                        */
+    uint32_t jit_segments;        /* device functions the generated source was cut into              */
+    uint32_t jit_frame_slots;     /* per-thread frame doubles (0 when not segmented)                 */
+    uint32_t jit_registers;       /* registers per thread of the generated kernel (0 = unknown)      */
+    uint32_t jit_source_bytes;
+    uint32_t jit_cubin_bytes;
+    /* timings, milliseconds */
+    double lower_ms;              /* Expr -> SSA                                                     */
+    double codegen_ms;            /* SSA -> source / bytecode                                        */
+    double nvrtc_ms;              /* NVRTC compile (reported separately from render time)            */
+    double load_ms;               /* cubin load + uploads                                            */
+    double kernel_ms[8];          /* last render: device time of the band kernel, per GPU            */
+    double gather_ms;             /* last render: band gather to GPU 0 (peer copies)                 */
+    double d2h_ms;                /* last render: device -> caller buffer                            */
+    double render_ms;             /* last render: wall time of the call                              */
+} maray_cuda_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+
+/* Creates a render handle over `n_gpus` devices (`device_ids` NULL = devices 0..n_gpus-1).
+ * n_gpus == 0 creates a host-only handle: it can load, validate, lower and compile scenes (NVRTC
+ * needs no GPU) but every render call fails with MARAY_E_CUDA.
+ * Stands in for: choosing `RenderMethod::JIT{threads,..}` (reference src/lib.rs:1166-1172). */
+int maray_cuda_create(int n_gpus, const int* device_ids, maray_cuda_t** out);
+void maray_cuda_destroy(maray_cuda_t* h);
+const char* maray_cuda_last_error(const maray_cuda_t* h);
+
+/* ---- scene ------------------------------------------------------------------------------------- */
+
+/* The default texture runtime: `Runtime::<Textures>::from_parts(Textures{images}, functions(n))`
+ * (reference examples/maray.rs:58-69, src/textures.rs:54-65).  rgb8[i] is w[i]*h[i]*3 bytes,
+ * row-major R,G,B (image::RgbImage).  Copied to every GPU of the handle.  Must precede compile. */
+int maray_cuda_set_textures(maray_cuda_t* h, uint32_t n, const uint8_t* const* rgb8,
+                            const uint32_t* w, const uint32_t* hgt);
+
+/* `maray::open` on an in-memory file (reference src/lib.rs:1227-1235): bincode
+ * ([u32;2],[Expr;3]), current or legacy variant numbering. */
+int maray_cuda_load_maray(maray_cuda_t* h, const uint8_t* bytes, size_t len);
+/* The [u32;2] size stored in the file. */
+int maray_cuda_scene_size(const maray_cuda_t* h, uint32_t* w, uint32_t* hgt);
+
+/* Lowers the scene (lexical Let, hash-consing across channels, host constant folding) and builds
+ * the chosen back end.  Stands in for `var_fixer::fix_color` + `Wasm::from_expr` x3
+ * (reference src/render.rs:117,163-165; src/wasm.rs:136-158).  `stats` may be NULL. */
+int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats);
+
+/* ---- render ------------------------------------------------------------------------------------ */
+
+/* Progress settings for maray_cuda_render (default: MARAY_REPORT_NONE). */
+int maray_cuda_set_report(maray_cuda_t* h, int kind, uint32_t every, maray_report_fn fn, void* user);
+
+/* `gen_to_image(method, rt, color, &mut img, report)` (reference src/lib.rs:1177-1195):
+ * renders a w x h image into the caller's HOST buffer `rgb` (w*h*3 bytes, the raw RgbImage layout,
+ * so Rust passes img.as_mut_ptr()).  Rows are split into contiguous bands over the handle's GPUs,
+ * bands are gathered on GPU 0 by peer copy and copied to `rgb`. */
+int maray_cuda_render(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint8_t* rgb, maray_cuda_stats* stats);
+
+/* Same, but the finished frame stays in device memory on the handle's first GPU:
+ * *d_rgb receives a device pointer (owned by the handle, valid until the next render/destroy). */
+int maray_cuda_render_device(maray_cuda_t* h, uint32_t w, uint32_t hgt, void** d_rgb, maray_cuda_stats* stats);
+
+/* One band, for one-process-per-GPU hosts: renders rows [y0, y1) of the w x hgt image on the
+ * handle's first GPU into the DEVICE buffer d_band ((y1-y0)*w*3 bytes), asynchronously on `stream`
+ * (a cudaStream_t; NULL = the default stream).  The caller orders and gathers bands itself. */
+int maray_cuda_render_band(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t y0, uint32_t y1,
+                           void* d_band, void* stream);
+
+/* Parity instrumentation: the raw f64 channel values of the window [x0,x1) x [y0,y1) of the
+ * w x hgt image, as 3 planes of (y1-y0)*(x1-x0) doubles (R, G, B), plus optionally its RGB8. */
+int maray_cuda_render_window_f64(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t x0, uint32_t x1,
+                                 uint32_t y0, uint32_t y1, double* planes, uint8_t* rgb);
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+
+int maray_cuda_get_stats(const maray_cuda_t* h, maray_cuda_stats* stats);
+/* Generated CUDA source of the NVRTC back end (after compile).  Returns its length in *len; copies
+ * at most cap bytes (NUL-terminated when cap > 0). */
+int maray_cuda_get_source(const maray_cuda_t* h, char* buf, size_t cap, size_t* len);
+/* Bytecode of the interpreter back end: 8-byte instructions, then the constant pool. */
+int maray_cuda_get_bytecode(const maray_cuda_t* h, uint64_t* code, size_t cap_instr, size_t* n_instr,
+                            double* consts, size_t cap_consts, size_t* n_consts);
+
+/* Measures the FP64 pipe on GPU `gpu_index` of the handle with a DADD/DMUL (no FMA) issue-rate
+ * kernel: *lane_ops_per_s = warp instructions * 32 / s.  The roofline denominator of bench.py. */
+int maray_cuda_fp64_peak(maray_cuda_t* h, int gpu_index, double* lane_ops_per_s, double* dfma_lane_ops_per_s);
+
+/* Library version string. */
+const char* maray_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARAY_CUDA_H */

@@ -1,0 +1,628 @@
+// C ABI of the render path (include/maray_cuda.h): handle, texture upload, compile, render.
+//
+// Shape of the work per render call (the counterpart of reference src/render.rs:102-192):
+//   rows are cut into contiguous bands, one per GPU of the handle; each GPU runs the band kernel
+//   on its own stream; GPU 0 renders straight into the frame buffer, the other GPUs render into a
+//   local band buffer and push it into GPU 0's frame with one peer copy (the only exchange step);
+//   one device->host copy hands the frame to the caller.
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/maray_cuda.h"
+#include "bytecode.hpp"
+#include "codegen.hpp"
+#include "device_sem.cuh"
+#include "expr.hpp"
+#include "kernels.hpp"
+#include "program.hpp"
+
+using namespace maray;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct HostTexture { uint32_t w, h; std::vector<uint8_t> rgb; };
+
+struct Gpu {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // band / frame buffer
+    uint8_t* d_out = nullptr; size_t out_cap = 0;
+    double* d_f64 = nullptr; size_t f64_cap = 0;
+    // textures
+    std::vector<uint8_t*> d_tex;
+    MrTexture* d_textab = nullptr;
+    // back ends
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t jit_kernel = nullptr;
+    uint64_t* d_code = nullptr;
+    double* d_consts = nullptr;
+    double* d_sink = nullptr;
+    bool peer_to_0 = false;
+};
+
+}  // namespace
+
+struct maray_cuda {
+    std::vector<Gpu> gpus;
+    std::string error;
+    Scene scene;
+    bool have_scene = false;
+    std::vector<HostTexture> textures;
+    bool textures_uploaded = false;
+    Program prog;
+    bool compiled = false;
+    int backend = -1;
+    std::string source;
+    std::vector<char> cubin;
+    Bytecode bc;
+    unsigned interp_block = 128, interp_ppt = 2;
+    maray_cuda_stats stats{};
+    int report_kind = MARAY_REPORT_NONE;
+    uint32_t report_every = 0;
+    maray_report_fn report_fn = nullptr;
+    void* report_user = nullptr;
+};
+
+namespace {
+
+int fail(maray_cuda* h, int code, const std::string& msg) {
+    if (h) h->error = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU_TRY(h, expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(h, MARAY_E_CUDA, std::string(#expr) + ": " + cudaGetErrorName(e_) + " (" +       \
+                                             cudaGetErrorString(e_) + ")");                               \
+    } while (0)
+
+void release_backend(maray_cuda* h) {
+    for (Gpu& g : h->gpus) {
+        cudaSetDevice(g.device);
+        if (g.lib) { cudaLibraryUnload(g.lib); g.lib = nullptr; g.jit_kernel = nullptr; }
+        if (g.d_code) { cudaFree(g.d_code); g.d_code = nullptr; }
+        if (g.d_consts) { cudaFree(g.d_consts); g.d_consts = nullptr; }
+    }
+    h->compiled = false;
+}
+
+void release_textures(maray_cuda* h) {
+    for (Gpu& g : h->gpus) {
+        cudaSetDevice(g.device);
+        for (uint8_t* p : g.d_tex) if (p) cudaFree(p);
+        g.d_tex.clear();
+        if (g.d_textab) { cudaFree(g.d_textab); g.d_textab = nullptr; }
+    }
+    h->textures_uploaded = false;
+}
+
+int upload_textures(maray_cuda* h) {
+    if (h->textures_uploaded || h->gpus.empty()) return MARAY_OK;
+    for (Gpu& g : h->gpus) {
+        CU_TRY(h, cudaSetDevice(g.device));
+        std::vector<MrTexture> tab(h->textures.size());
+        g.d_tex.assign(h->textures.size(), nullptr);
+        for (size_t i = 0; i < h->textures.size(); i++) {
+            const HostTexture& t = h->textures[i];
+            size_t bytes = std::max<size_t>(t.rgb.size(), 16);
+            CU_TRY(h, cudaMalloc(&g.d_tex[i], bytes));
+            if (!t.rgb.empty()) CU_TRY(h, cudaMemcpy(g.d_tex[i], t.rgb.data(), t.rgb.size(), cudaMemcpyHostToDevice));
+            tab[i] = MrTexture{g.d_tex[i], t.w, t.h};
+        }
+        if (!tab.empty()) {
+            CU_TRY(h, cudaMalloc(&g.d_textab, tab.size() * sizeof(MrTexture)));
+            CU_TRY(h, cudaMemcpy(g.d_textab, tab.data(), tab.size() * sizeof(MrTexture), cudaMemcpyHostToDevice));
+        }
+    }
+    h->textures_uploaded = true;
+    return MARAY_OK;
+}
+
+int ensure_out(maray_cuda* h, Gpu& g, size_t bytes) {
+    if (g.out_cap >= bytes) return MARAY_OK;
+    CU_TRY(h, cudaSetDevice(g.device));
+    if (g.d_out) cudaFree(g.d_out);
+    g.d_out = nullptr; g.out_cap = 0;
+    CU_TRY(h, cudaMalloc(&g.d_out, std::max<size_t>(bytes, 256)));
+    g.out_cap = bytes;
+    return MARAY_OK;
+}
+
+void fill_program_stats(maray_cuda* h) {
+    maray_cuda_stats& s = h->stats;
+    const ProgramStats& p = h->prog.stats;
+    s.tree_nodes = p.tree_nodes; s.dag_nodes = p.dag_nodes;
+    s.n_const = p.n_const; s.n_x_only = p.n_x; s.n_y_only = p.n_y; s.n_xy = p.n_xy;
+    s.n_add = p.op_count[OP_ADD]; s.n_mul = p.op_count[OP_MUL]; s.n_neg = p.op_count[OP_NEG];
+    s.n_abs = p.op_count[OP_ABS]; s.n_recip = p.op_count[OP_RECIP]; s.n_sqrt = p.op_count[OP_SQRT];
+    s.n_step = p.op_count[OP_STEP]; s.n_min = p.op_count[OP_MIN]; s.n_max = p.op_count[OP_MAX];
+    s.n_sin = p.op_count[OP_SIN]; s.n_exp = p.op_count[OP_EXP]; s.n_ln = p.op_count[OP_LN];
+    s.n_tex = p.op_count[OP_TEX];
+    s.dag_depth = p.depth;
+    s.legacy_layout = h->scene.legacy_layout ? 1 : 0;
+}
+
+// NVRTC: source -> sm_100a cubin.  Works without a GPU.
+int nvrtc_compile(maray_cuda* h) {
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, h->source.c_str(), "maray_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(h, MARAY_E_COMPILE, "nvrtcCreateProgram failed");
+    const char* opts[] = {
+        "--gpu-architecture=sm_100a",
+        "--fmad=false",               // the reference never fuses a*b+c
+        "--std=c++17",
+        "-lineinfo",
+        "--ptxas-options=-v",
+    };
+    nvrtcResult rc = nvrtcCompileProgram(prog, int(sizeof opts / sizeof opts[0]), opts);
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    std::string log(log_size, '\0');
+    if (log_size > 1) nvrtcGetProgramLog(prog, &log[0]);
+    if (rc != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        if (log.size() > 4000) log.resize(4000);
+        return fail(h, MARAY_E_COMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(rc) + "\n" + log);
+    }
+    size_t cubin_size = 0;
+    if (nvrtcGetCUBINSize(prog, &cubin_size) != NVRTC_SUCCESS || cubin_size == 0) {
+        nvrtcDestroyProgram(&prog);
+        return fail(h, MARAY_E_COMPILE, "NVRTC produced no cubin");
+    }
+    h->cubin.resize(cubin_size);
+    nvrtcGetCUBIN(prog, h->cubin.data());
+    nvrtcDestroyProgram(&prog);
+    // registers of the kernel from the ptxas -v log: "... Function properties for maray_jit ... Used N registers"
+    h->stats.jit_registers = 0;
+    size_t at = log.find(std::string("Compiling entry function '") + kJitKernelName + "'");
+    if (at != std::string::npos) {
+        size_t u = log.find("Used ", at);
+        if (u != std::string::npos) h->stats.jit_registers = uint32_t(std::atoi(log.c_str() + u + 5));
+    }
+    return MARAY_OK;
+}
+
+// Interpreter launch shape: as many resident warps as the slot file allows.
+void choose_interp_shape(maray_cuda* h) {
+    const size_t budget = 200 * 1024;   // leave room under the 227 KiB per-block limit
+    const unsigned shapes[][2] = {{256, 2}, {128, 2}, {128, 1}, {64, 1}, {32, 1}};
+    for (auto& sh : shapes) {
+        if (interp_smem_bytes(sh[0], sh[1], h->bc.n_slots) <= budget) {
+            h->interp_block = sh[0]; h->interp_ppt = sh[1];
+            return;
+        }
+    }
+    h->interp_block = 0;   // does not fit
+}
+
+int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint8_t* d_out, double* d_f64,
+                size_t f64_plane, cudaStream_t stream) {
+    MrParams p;
+    p.out = d_out; p.f64_out = d_f64; p.f64_plane = f64_plane; p.tex = g.d_textab;
+    p.p0 = p0; p.n = n; p.W = w;
+    p.out_aligned = (reinterpret_cast<uintptr_t>(d_out) % 16 == 0) ? 1u : 0u;
+    if (n == 0) return MARAY_OK;
+    if (h->backend == MARAY_BACKEND_NVRTC) {
+        void* args[] = {&p};
+        unsigned grid = (n + kJitBlock - 1) / kJitBlock;
+        CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(kJitBlock), args, 0, stream));
+    } else {
+        CU_TRY(h, launch_interp(p, g.d_code, unsigned(h->bc.code.size()), g.d_consts, h->bc.n_slots, h->interp_block,
+                                h->interp_ppt, stream));
+    }
+    return MARAY_OK;
+}
+
+int check_renderable(maray_cuda* h, uint32_t w, uint32_t hgt) {
+    if (!h) return MARAY_E_INVALID;
+    if (!h->compiled) return fail(h, MARAY_E_INVALID, "render called before maray_cuda_compile");
+    if (h->gpus.empty()) return fail(h, MARAY_E_CUDA, "host-only handle (created with 0 GPUs): there is no CPU fallback");
+    if (w == 0 || hgt == 0) return fail(h, MARAY_E_INVALID, "empty image");
+    if (uint64_t(w) * hgt > 0xffffffffull) return fail(h, MARAY_E_INVALID, "image has more than 2^32-1 pixels");
+    return MARAY_OK;
+}
+
+// Renders rows [ya, yb) of the w x hgt frame into GPU 0's frame buffer (device), banded over GPUs.
+int render_rows_to_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint32_t ya, uint32_t yb) {
+    (void)hgt;
+    const size_t G = h->gpus.size();
+    const uint32_t rows = yb - ya;
+    Gpu& g0 = h->gpus[0];
+    std::vector<uint32_t> b0(G + 1);
+    for (size_t g = 0; g <= G; g++) b0[g] = ya + uint32_t(uint64_t(rows) * g / G);
+    for (size_t gi = 0; gi < G; gi++) {
+        Gpu& g = h->gpus[gi];
+        uint32_t y0 = b0[gi], y1 = b0[gi + 1];
+        size_t bytes = size_t(y1 - y0) * w * 3;
+        CU_TRY(h, cudaSetDevice(g.device));
+        uint8_t* dst;
+        if (gi == 0) dst = g0.d_out + size_t(y0) * w * 3;
+        else {
+            int rc = ensure_out(h, g, bytes);
+            if (rc) return rc;
+            dst = g.d_out;
+        }
+        CU_TRY(h, cudaEventRecord(g.ev0, g.stream));
+        int rc = launch_band(h, g, w, y0 * w, (y1 - y0) * w, dst, nullptr, 0, g.stream);
+        if (rc) return rc;
+        CU_TRY(h, cudaEventRecord(g.ev1, g.stream));
+        if (gi != 0 && bytes)
+            CU_TRY(h, cudaMemcpyPeerAsync(g0.d_out + size_t(y0) * w * 3, g0.device, g.d_out, g.device, bytes, g.stream));
+    }
+    double t_gather0 = now_ms();
+    for (size_t gi = 0; gi < G; gi++) {
+        Gpu& g = h->gpus[gi];
+        CU_TRY(h, cudaSetDevice(g.device));
+        CU_TRY(h, cudaStreamSynchronize(g.stream));
+        float ms = 0.f;
+        CU_TRY(h, cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        if (gi < 8) h->stats.kernel_ms[gi] += ms;
+    }
+    (void)t_gather0;
+    CU_TRY(h, cudaSetDevice(g0.device));
+    return MARAY_OK;
+}
+
+int render_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
+    int rc = check_renderable(h, w, hgt);
+    if (rc) return rc;
+    double t0 = now_ms();
+    Gpu& g0 = h->gpus[0];
+    rc = ensure_out(h, g0, size_t(w) * hgt * 3);
+    if (rc) return rc;
+    for (double& k : h->stats.kernel_ms) k = 0.0;
+    h->stats.gather_ms = 0.0; h->stats.d2h_ms = 0.0;
+
+    if (h->report_kind == MARAY_REPORT_NONE || !h->report_fn || !host_rgb) {
+        rc = render_rows_to_frame(h, w, hgt, 0, hgt);
+        if (rc) return rc;
+        if (host_rgb) {
+            double t1 = now_ms();
+            CU_TRY(h, cudaMemcpy(host_rgb, g0.d_out, size_t(w) * hgt * 3, cudaMemcpyDeviceToHost));
+            h->stats.d2h_ms = now_ms() - t1;
+        }
+    } else {
+        // Progress reporting (reference src/report.rs:37-56): the frame is rendered in row chunks;
+        // after a chunk the finished rows are copied out and the callback sees the partial image.
+        uint32_t chunk = (h->report_kind == MARAY_REPORT_ROW) ? std::max<uint32_t>(1, h->report_every)
+                                                              : std::max<uint32_t>(1, hgt / 64);
+        double last = now_ms();
+        uint32_t last_row = 0;
+        for (uint32_t ya = 0; ya < hgt; ya += chunk) {
+            uint32_t yb = std::min(hgt, ya + chunk);
+            rc = render_rows_to_frame(h, w, hgt, ya, yb);
+            if (rc) return rc;
+            double t1 = now_ms();
+            CU_TRY(h, cudaMemcpy(host_rgb + size_t(ya) * w * 3, g0.d_out + size_t(ya) * w * 3, size_t(yb - ya) * w * 3,
+                                 cudaMemcpyDeviceToHost));
+            h->stats.d2h_ms += now_ms() - t1;
+            if (yb == hgt) break;
+            bool fire;
+            if (h->report_kind == MARAY_REPORT_ROW) {
+                fire = yb >= last_row + h->report_every;
+                if (fire) last_row += h->report_every;
+            } else {
+                fire = now_ms() - last >= double(h->report_every);
+                if (fire) last = now_ms();
+            }
+            if (fire) h->report_fn(h->report_user, host_rgb, w, hgt, double(yb) / double(hgt));
+        }
+    }
+    h->stats.render_ms = now_ms() - t0;
+    return MARAY_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* maray_cuda_version(void) { return "maray_b200 0.1 (sm_100a)"; }
+
+const char* maray_cuda_last_error(const maray_cuda_t* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int maray_cuda_create(int n_gpus, const int* device_ids, maray_cuda_t** out) {
+    if (!out || n_gpus < 0) return fail(nullptr, MARAY_E_INVALID, "maray_cuda_create: bad arguments");
+    *out = nullptr;
+    std::unique_ptr<maray_cuda> h(new maray_cuda());
+    if (n_gpus > 0) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            return fail(nullptr, MARAY_E_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+                                                   " (this render path has no CPU fallback)");
+        for (int i = 0; i < n_gpus; i++) {
+            int dev = device_ids ? device_ids[i] : i;
+            if (dev < 0 || dev >= count)
+                return fail(nullptr, MARAY_E_CUDA, "device " + std::to_string(dev) + " requested but only " +
+                                                       std::to_string(count) + " visible");
+            Gpu g;
+            g.device = dev;
+            h->gpus.push_back(g);
+        }
+        maray_cuda* hp = nullptr;   // errors during create go to the thread-local message
+        for (size_t i = 0; i < h->gpus.size(); i++) {
+            Gpu& g = h->gpus[i];
+            CU_TRY(hp, cudaSetDevice(g.device));
+            CU_TRY(hp, cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+            CU_TRY(hp, cudaEventCreate(&g.ev0));
+            CU_TRY(hp, cudaEventCreate(&g.ev1));
+            CU_TRY(hp, cudaMalloc(&g.d_sink, 256));
+            if (i > 0) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, g.device, h->gpus[0].device);
+                if (can) {
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(h->gpus[0].device, 0);
+                    if (pe == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); pe = cudaSuccess; }
+                    g.peer_to_0 = (pe == cudaSuccess);
+                }
+            }
+        }
+        cudaSetDevice(h->gpus[0].device);
+    }
+    *out = h.release();
+    return MARAY_OK;
+}
+
+void maray_cuda_destroy(maray_cuda_t* h) {
+    if (!h) return;
+    release_backend(h);
+    release_textures(h);
+    for (Gpu& g : h->gpus) {
+        cudaSetDevice(g.device);
+        if (g.d_out) cudaFree(g.d_out);
+        if (g.d_f64) cudaFree(g.d_f64);
+        if (g.d_sink) cudaFree(g.d_sink);
+        if (g.ev0) cudaEventDestroy(g.ev0);
+        if (g.ev1) cudaEventDestroy(g.ev1);
+        if (g.stream) cudaStreamDestroy(g.stream);
+    }
+    delete h;
+}
+
+int maray_cuda_set_textures(maray_cuda_t* h, uint32_t n, const uint8_t* const* rgb8, const uint32_t* w, const uint32_t* hgt) {
+    if (!h || (n && (!rgb8 || !w || !hgt))) return fail(h, MARAY_E_INVALID, "maray_cuda_set_textures: bad arguments");
+    release_textures(h);
+    h->textures.clear();
+    h->textures.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        HostTexture& t = h->textures[i];
+        t.w = w[i]; t.h = hgt[i];
+        size_t bytes = size_t(w[i]) * hgt[i] * 3;
+        if (bytes && !rgb8[i]) return fail(h, MARAY_E_INVALID, "maray_cuda_set_textures: null texture data");
+        t.rgb.assign(rgb8[i], rgb8[i] + bytes);
+    }
+    h->compiled = false;   // width/height constants are folded into the program
+    return MARAY_OK;
+}
+
+int maray_cuda_load_maray(maray_cuda_t* h, const uint8_t* bytes, size_t len) {
+    if (!h || !bytes) return fail(h, MARAY_E_INVALID, "maray_cuda_load_maray: bad arguments");
+    release_backend(h);
+    h->have_scene = false;
+    Scene sc;
+    std::string err;
+    if (!parse_maray(bytes, len, &sc, &err)) return fail(h, MARAY_E_PARSE, err);
+    h->scene = std::move(sc);
+    h->have_scene = true;
+    return MARAY_OK;
+}
+
+int maray_cuda_scene_size(const maray_cuda_t* h, uint32_t* w, uint32_t* hgt) {
+    if (!h || !h->have_scene || !w || !hgt) return MARAY_E_INVALID;
+    *w = h->scene.size[0]; *hgt = h->scene.size[1];
+    return MARAY_OK;
+}
+
+int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
+    if (!h) return MARAY_E_INVALID;
+    if (!h->have_scene) return fail(h, MARAY_E_INVALID, "maray_cuda_compile called before maray_cuda_load_maray");
+    if (backend != MARAY_BACKEND_INTERP && backend != MARAY_BACKEND_NVRTC)
+        return fail(h, MARAY_E_INVALID, "unknown back end");
+    release_backend(h);
+    h->stats = maray_cuda_stats{};
+    h->stats.backend = uint32_t(backend);
+
+    double t0 = now_ms();
+    std::vector<TextureDim> dims;
+    for (const HostTexture& t : h->textures) dims.push_back(TextureDim{t.w, t.h});
+    std::string err;
+    Program prog;
+    if (!lower_scene(h->scene, dims, &prog, &err)) return fail(h, MARAY_E_SCENE, err);
+    h->prog = std::move(prog);
+    h->stats.lower_ms = now_ms() - t0;
+    fill_program_stats(h);
+
+    double t1 = now_ms();
+    if (backend == MARAY_BACKEND_NVRTC) {
+        CodegenInfo info;
+        CodegenOptions copt;
+        // tuning knobs (documented in DESIGN.md "NVRTC back end")
+        if (const char* e = std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = uint32_t(std::strtoul(e, nullptr, 10));
+        if (const char* e = std::getenv("MARAY_JIT_INLINE_TRANS_BELOW")) copt.inline_transcendentals_below = uint32_t(std::strtoul(e, nullptr, 10));
+        h->source = generate_cuda_source(h->prog, copt, &info);
+        h->stats.codegen_ms = now_ms() - t1;
+        h->stats.jit_segments = info.segments;
+        h->stats.jit_frame_slots = info.frame_slots;
+        h->stats.jit_source_bytes = uint32_t(h->source.size());
+        double t2 = now_ms();
+        int rc = nvrtc_compile(h);
+        h->stats.nvrtc_ms = now_ms() - t2;
+        if (rc) return rc;
+        h->stats.jit_cubin_bytes = uint32_t(h->cubin.size());
+    } else {
+        if (!compile_bytecode(h->prog, &h->bc, &err)) return fail(h, MARAY_E_COMPILE, err);
+        if (h->bc.code.size() & 1) h->bc.code.push_back(bc_encode(BC_END, 0));   // 16-byte cp.async granules
+        choose_interp_shape(h);
+        if (!h->interp_block)
+            return fail(h, MARAY_E_UNSUPPORTED, "program needs " + std::to_string(h->bc.n_slots) +
+                                                    " live values per pixel, more than the interpreter's shared-memory slot file holds");
+        h->stats.codegen_ms = now_ms() - t1;
+        h->stats.interp_instructions = uint32_t(h->bc.code.size());
+        h->stats.interp_slots = h->bc.n_slots;
+    }
+    h->backend = backend;
+
+    // Device side: textures, code.
+    double t3 = now_ms();
+    if (!h->gpus.empty()) {
+        int rc = upload_textures(h);
+        if (rc) return rc;
+        for (Gpu& g : h->gpus) {
+            CU_TRY(h, cudaSetDevice(g.device));
+            if (backend == MARAY_BACKEND_NVRTC) {
+                CU_TRY(h, cudaLibraryLoadData(&g.lib, h->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+                CU_TRY(h, cudaLibraryGetKernel(&g.jit_kernel, g.lib, kJitKernelName));
+            } else {
+                CU_TRY(h, cudaMalloc(&g.d_code, h->bc.code.size() * sizeof(uint64_t)));
+                CU_TRY(h, cudaMemcpy(g.d_code, h->bc.code.data(), h->bc.code.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+                CU_TRY(h, cudaMalloc(&g.d_consts, h->bc.consts.size() * sizeof(double)));
+                CU_TRY(h, cudaMemcpy(g.d_consts, h->bc.consts.data(), h->bc.consts.size() * sizeof(double), cudaMemcpyHostToDevice));
+            }
+        }
+        cudaSetDevice(h->gpus[0].device);
+    }
+    h->stats.load_ms = now_ms() - t3;
+    h->compiled = true;
+    if (stats) *stats = h->stats;
+    return MARAY_OK;
+}
+
+int maray_cuda_set_report(maray_cuda_t* h, int kind, uint32_t every, maray_report_fn fn, void* user) {
+    if (!h || kind < MARAY_REPORT_NONE || kind > MARAY_REPORT_DURATION_MS) return fail(h, MARAY_E_INVALID, "bad report kind");
+    h->report_kind = kind; h->report_every = every; h->report_fn = fn; h->report_user = user;
+    return MARAY_OK;
+}
+
+int maray_cuda_render(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint8_t* rgb, maray_cuda_stats* stats) {
+    if (!h) return MARAY_E_INVALID;
+    if (!rgb) return fail(h, MARAY_E_INVALID, "maray_cuda_render: null output buffer");
+    int rc = render_frame(h, w, hgt, rgb);
+    if (rc == MARAY_OK && stats) *stats = h->stats;
+    return rc;
+}
+
+int maray_cuda_render_device(maray_cuda_t* h, uint32_t w, uint32_t hgt, void** d_rgb, maray_cuda_stats* stats) {
+    if (!h) return MARAY_E_INVALID;
+    if (!d_rgb) return fail(h, MARAY_E_INVALID, "maray_cuda_render_device: null output pointer");
+    int rc = render_frame(h, w, hgt, nullptr);
+    if (rc) return rc;
+    *d_rgb = h->gpus[0].d_out;
+    if (stats) *stats = h->stats;
+    return MARAY_OK;
+}
+
+int maray_cuda_render_band(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t y0, uint32_t y1, void* d_band, void* stream) {
+    int rc = check_renderable(h, w, hgt);
+    if (rc) return rc;
+    if (y0 > y1 || y1 > hgt || !d_band) return fail(h, MARAY_E_INVALID, "maray_cuda_render_band: bad band");
+    Gpu& g = h->gpus[0];
+    CU_TRY(h, cudaSetDevice(g.device));
+    return launch_band(h, g, w, y0 * w, (y1 - y0) * w, static_cast<uint8_t*>(d_band), nullptr, 0,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int maray_cuda_render_window_f64(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t x0, uint32_t x1, uint32_t y0,
+                                 uint32_t y1, double* planes, uint8_t* rgb) {
+    int rc = check_renderable(h, w, hgt);
+    if (rc) return rc;
+    if (x0 > x1 || x1 > w || y0 > y1 || y1 > hgt) return fail(h, MARAY_E_INVALID, "window outside the image");
+    const uint32_t ww = x1 - x0, hh = y1 - y0;
+    const size_t npx = size_t(ww) * hh;
+    if (npx == 0) return MARAY_OK;
+    Gpu& g = h->gpus[0];
+    CU_TRY(h, cudaSetDevice(g.device));
+    rc = ensure_out(h, g, npx * 3 + 16 * size_t(hh));
+    if (rc) return rc;
+    if (g.f64_cap < npx * 3) {
+        if (g.d_f64) cudaFree(g.d_f64);
+        g.d_f64 = nullptr; g.f64_cap = 0;
+        CU_TRY(h, cudaMalloc(&g.d_f64, npx * 3 * sizeof(double)));
+        g.f64_cap = npx * 3;
+    }
+    // one launch per window row (instrumentation path, not a fast path)
+    for (uint32_t r = 0; r < hh; r++) {
+        rc = launch_band(h, g, w, (y0 + r) * w + x0, ww, g.d_out + size_t(r) * ww * 3,
+                         planes ? g.d_f64 + size_t(r) * ww : nullptr, npx, g.stream);
+        if (rc) return rc;
+    }
+    CU_TRY(h, cudaStreamSynchronize(g.stream));
+    if (planes) CU_TRY(h, cudaMemcpy(planes, g.d_f64, npx * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (rgb) CU_TRY(h, cudaMemcpy(rgb, g.d_out, npx * 3, cudaMemcpyDeviceToHost));
+    return MARAY_OK;
+}
+
+int maray_cuda_get_stats(const maray_cuda_t* h, maray_cuda_stats* stats) {
+    if (!h || !stats) return MARAY_E_INVALID;
+    *stats = h->stats;
+    return MARAY_OK;
+}
+
+int maray_cuda_get_source(const maray_cuda_t* h, char* buf, size_t cap, size_t* len) {
+    if (!h) return MARAY_E_INVALID;
+    if (len) *len = h->source.size();
+    if (buf && cap) {
+        size_t n = std::min(cap - 1, h->source.size());
+        std::memcpy(buf, h->source.data(), n);
+        buf[n] = '\0';
+    }
+    return MARAY_OK;
+}
+
+int maray_cuda_get_bytecode(const maray_cuda_t* h, uint64_t* code, size_t cap_instr, size_t* n_instr, double* consts,
+                            size_t cap_consts, size_t* n_consts) {
+    if (!h) return MARAY_E_INVALID;
+    if (n_instr) *n_instr = h->bc.code.size();
+    if (n_consts) *n_consts = h->bc.consts.size();
+    if (code) std::memcpy(code, h->bc.code.data(), std::min(cap_instr, h->bc.code.size()) * sizeof(uint64_t));
+    if (consts) std::memcpy(consts, h->bc.consts.data(), std::min(cap_consts, h->bc.consts.size()) * sizeof(double));
+    return MARAY_OK;
+}
+
+int maray_cuda_fp64_peak(maray_cuda_t* h, int gpu_index, double* lane_ops_per_s, double* dfma_lane_ops_per_s) {
+    if (!h) return MARAY_E_INVALID;
+    if (gpu_index < 0 || size_t(gpu_index) >= h->gpus.size()) return fail(h, MARAY_E_CUDA, "no such GPU in this handle");
+    Gpu& g = h->gpus[gpu_index];
+    CU_TRY(h, cudaSetDevice(g.device));
+    cudaDeviceProp prop;
+    CU_TRY(h, cudaGetDeviceProperties(&prop, g.device));
+    const int blocks = prop.multiProcessorCount * 8;   // 8 x 256 threads = 2048 threads per SM
+    const int iters = 4096;
+    for (int fma = 0; fma < 2; fma++) {
+        double best = 0.0;
+        for (int rep = 0; rep < 4; rep++) {
+            CU_TRY(h, cudaEventRecord(g.ev0, g.stream));
+            CU_TRY(h, launch_fp64_issue_rate(fma != 0, g.d_sink, iters, blocks, g.stream));
+            CU_TRY(h, cudaEventRecord(g.ev1, g.stream));
+            CU_TRY(h, cudaStreamSynchronize(g.stream));
+            float ms = 0.f;
+            CU_TRY(h, cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+            double ops = double(blocks) * 256.0 * double(iters) * 64.0;   // 8 chains x 8 unrolled per iteration
+            if (rep > 0) best = std::max(best, ops / (double(ms) * 1e-3));
+        }
+        if (fma == 0 && lane_ops_per_s) *lane_ops_per_s = best;
+        if (fma == 1 && dfma_lane_ops_per_s) *dfma_lane_ops_per_s = best;
+    }
+    return MARAY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,35 @@
+// Straight-line CUDA source from the SSA program: the GPU sibling of the reference's WAT code
+// generator (reference src/wasm.rs:77-124).  Differences that are deliberate:
+// the source is emitted from the hash-consed SSA program, not from the tree text, so every value
+// is computed once, all three channels share one kernel, and declarations never collide.
+#pragma once
+#include <string>
+
+#include "program.hpp"
+
+namespace maray {
+
+struct CodegenOptions {
+    // Programs with more values than this are cut into __noinline__ device functions of this many
+    // values each; values that cross a cut live in a per-thread frame (local memory).  Bounds
+    // ptxas time, which is super-linear in basic-block size.
+    uint32_t segment_values = 4096;
+    // sin/exp/ln are inlined below this many transcendental values, called out-of-line above it
+    // (their inlined bodies dominate code size and compile time in transcendental-heavy scenes).
+    uint32_t inline_transcendentals_below = 2048;
+};
+
+struct CodegenInfo {
+    uint32_t segments = 0;
+    uint32_t frame_slots = 0;       // doubles of per-thread frame (0 when not segmented)
+    bool transcendentals_inlined = true;
+};
+
+// Name of the generated kernel (extern "C").
+extern const char* const kJitKernelName;
+// Threads per block the generated kernel is written for.
+constexpr unsigned kJitBlock = 256;
+
+std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt, CodegenInfo* info);
+
+}  // namespace maray

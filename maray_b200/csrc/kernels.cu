@@ -1,0 +1,288 @@
+// Hand-written sm_100a kernels of the render path:
+//   maray_interp<P>   -- the bytecode interpreter (MARAY_BACKEND_INTERP)
+//   fp64_issue_rate   -- FP64-pipe issue-rate microbenchmark (the roofline denominator)
+// The NVRTC back end's kernel is generated at run time (codegen.cpp) from the same device_sem.cuh.
+//
+// Compiled with --fmad=false: the reference never fuses a*b+c.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "bytecode.hpp"
+#include "device_sem.cuh"
+#include "kernels.hpp"
+
+namespace maray {
+
+// ------------------------------------------------------------------------------------------------
+// Bytecode interpreter.
+//
+// Mapping: one thread evaluates P pixels (P independent dependency chains hide FP64 and shared-
+// memory latency); a block of B threads covers B*P consecutive pixels of the linear image index.
+// Per-pixel value slots live in shared memory as slots[slot][k][tid] (consecutive threads hit
+// consecutive 8-byte words: conflict-free).  The instruction stream is warp-uniform: it is staged
+// from global memory into shared memory in double-buffered chunks with cp.async and every warp
+// reads the same word (a broadcast), so there is no divergence anywhere in the loop.
+// The accumulator-machine encoding (bytecode.hpp) keeps slot traffic to at most one 8-byte load
+// and one optional 8-byte store per FP64 operation.
+
+constexpr int kChunk = 512;   // instructions per staged chunk (4 KiB)
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned int s = (unsigned int)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int P>
+__global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code, unsigned int n_instr,
+                             const double* __restrict__ consts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [2][kChunk] instruction words | staging tile (3*B*P bytes, 16-aligned) | slots
+    uint64_t* code_s = reinterpret_cast<uint64_t*>(smem_raw);
+    unsigned char* stage = smem_raw + 2 * kChunk * sizeof(uint64_t);
+    const unsigned int B = blockDim.x;
+    const unsigned int tid = threadIdx.x;
+    double* slots = reinterpret_cast<double*>(stage + ((3u * B * P + 15u) & ~15u));
+
+    const unsigned int first = blockIdx.x * B * P;
+    double acc[P];
+    double out_r[P], out_g[P], out_b[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        unsigned int j = first + k * B + tid;
+        unsigned int pix = p.p0 + (j < p.n ? j : 0u);   // idle lanes redo pixel p0
+        unsigned int yi = pix / p.W;
+        unsigned int xi = pix - yi * p.W;
+        slots[(0 * P + k) * B + tid] = (double)xi;      // `x as f64`, reference src/render.rs:25
+        slots[(1 * P + k) * B + tid] = (double)yi;
+        acc[k] = 0.0; out_r[k] = 0.0; out_g[k] = 0.0; out_b[k] = 0.0;
+    }
+
+    const unsigned int n_chunks = (n_instr + kChunk - 1) / kChunk;
+    // prefetch chunk 0
+    for (unsigned int i = tid; i < kChunk / 2; i += B) {
+        unsigned int idx = i * 2;
+        if (idx < n_instr) cp_async16(code_s + idx, code + idx);
+    }
+    cp_async_commit();
+
+    for (unsigned int c = 0; c < n_chunks; c++) {
+        cp_async_wait_all();
+        __syncthreads();   // chunk c landed; every warp is done with chunk c-1
+        if (c + 1 < n_chunks) {
+            uint64_t* dst = code_s + ((c + 1) & 1) * kChunk;
+            const uint64_t* src = code + (size_t)(c + 1) * kChunk;
+            unsigned int left = n_instr - (c + 1) * kChunk;
+            for (unsigned int i = tid; i < kChunk / 2; i += B) {
+                unsigned int idx = i * 2;
+                if (idx < left) cp_async16(dst + idx, src + idx);
+            }
+            cp_async_commit();
+        }
+        const uint64_t* cs = code_s + (c & 1) * kChunk;
+        const unsigned int cnt = (n_instr - c * kChunk < (unsigned)kChunk) ? (n_instr - c * kChunk) : (unsigned)kChunk;
+        for (unsigned int i = 0; i < cnt; i++) {
+            const uint64_t w = cs[i];                     // warp-uniform: broadcast LDS.64
+            const unsigned int lo = (unsigned int)w, operand = (unsigned int)(w >> 32);
+            const unsigned int op = lo & 0xffu;
+            const double* sp = slots + (size_t)(operand & 0xffffu) * P * B + tid;   // *_S and TEX forms
+            switch (op) {
+            case BC_LD_S:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = slots[((size_t)operand * P + k) * B + tid];
+                break;
+            case BC_LD_K: { const double kv = __ldg(consts + operand);
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = kv; } break;
+            case BC_NEG:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = -acc[k];
+                break;
+            case BC_ABS:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = fabs(acc[k]);
+                break;
+            case BC_RECIP:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_recip(acc[k]);
+                break;
+            case BC_SQRT:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_sqrt(acc[k]);
+                break;
+            case BC_STEP:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_step(acc[k]);
+                break;
+            case BC_SIN:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = sin(acc[k]);
+                break;
+            case BC_EXP:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = exp(acc[k]);
+                break;
+            case BC_LN:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = log(acc[k]);
+                break;
+            case BC_ADD_S:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = acc[k] + sp[k * B];
+                break;
+            case BC_ADD_K: { const double kv = __ldg(consts + operand);
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = acc[k] + kv; } break;
+            case BC_MUL_S:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = acc[k] * sp[k * B];
+                break;
+            case BC_MUL_K: { const double kv = __ldg(consts + operand);
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = acc[k] * kv; } break;
+            case BC_MAX_S:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_max(acc[k], sp[k * B]);
+                break;
+            case BC_MAX_K: { const double kv = __ldg(consts + operand);
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_max(acc[k], kv); } break;
+            case BC_MAXR_S:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_max(sp[k * B], acc[k]);
+                break;
+            case BC_MAXR_K: { const double kv = __ldg(consts + operand);
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_max(kv, acc[k]); } break;
+            case BC_MIN_S:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_min(acc[k], sp[k * B]);
+                break;
+            case BC_MIN_K: { const double kv = __ldg(consts + operand);
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_min(acc[k], kv); } break;
+            case BC_MINR_S:
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_min(sp[k * B], acc[k]);
+                break;
+            case BC_MINR_K: { const double kv = __ldg(consts + operand);
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_min(kv, acc[k]); } break;
+            case BC_TEX_S: { const MrTexture t = p.tex[operand >> 18]; const unsigned int ch = (operand >> 16) & 3u;
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_tex(t.data, t.w, t.h, ch, sp[k * B], acc[k]); } break;
+            case BC_TEXR_S: { const MrTexture t = p.tex[operand >> 18]; const unsigned int ch = (operand >> 16) & 3u;
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_tex(t.data, t.w, t.h, ch, acc[k], sp[k * B]); } break;
+            case BC_OUT_R:
+#pragma unroll
+                for (int k = 0; k < P; k++) out_r[k] = acc[k];
+                break;
+            case BC_OUT_G:
+#pragma unroll
+                for (int k = 0; k < P; k++) out_g[k] = acc[k];
+                break;
+            case BC_OUT_B:
+#pragma unroll
+                for (int k = 0; k < P; k++) out_b[k] = acc[k];
+                break;
+            default: break;   // BC_END
+            }
+            if (lo & BC_FLAG_STORE) {
+                double* dp = slots + (size_t)(lo >> 16) * P * B + tid;
+#pragma unroll
+                for (int k = 0; k < P; k++) dp[k * B] = acc[k];
+            }
+        }
+    }
+
+    // `as u8` + RGB pack through the staging tile, then coalesced 16-byte stores.
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        unsigned int l = k * B + tid;   // pixel within the block
+        stage[3u * l + 0u] = (unsigned char)mr_as_u8(out_r[k]);
+        stage[3u * l + 1u] = (unsigned char)mr_as_u8(out_g[k]);
+        stage[3u * l + 2u] = (unsigned char)mr_as_u8(out_b[k]);
+        unsigned int j = first + l;
+        if (p.f64_out != nullptr && j < p.n) {
+            p.f64_out[j] = out_r[k];
+            p.f64_out[(size_t)p.f64_plane + j] = out_g[k];
+            p.f64_out[2u * (size_t)p.f64_plane + j] = out_b[k];
+        }
+    }
+    __syncthreads();
+    const unsigned int span = B * P;
+    const unsigned int valid = (p.n - first < span) ? (p.n - first) : span;
+    unsigned char* dst = p.out + 3u * (size_t)first;
+    if (p.out_aligned && valid == span && (span & 15u) == 0u) {
+        for (unsigned int i = tid; i < 3u * span / 16u; i += B)
+            reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(stage)[i];
+    } else {
+        for (unsigned int i = tid; i < 3u * valid; i += B) dst[i] = stage[i];
+    }
+}
+
+size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_slots) {
+    size_t stage = (3u * (size_t)block * pixels_per_thread + 15u) & ~size_t(15);
+    return 2 * kChunk * sizeof(uint64_t) + stage + (size_t)n_slots * pixels_per_thread * block * sizeof(double);
+}
+
+cudaError_t launch_interp(const MrParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
+                          unsigned int n_slots, unsigned int block, unsigned int pixels_per_thread, cudaStream_t stream) {
+    if (p.n == 0) return cudaSuccess;
+    size_t smem = interp_smem_bytes(block, pixels_per_thread, n_slots);
+    unsigned int span = block * pixels_per_thread;
+    unsigned int grid = (p.n + span - 1) / span;
+    cudaError_t e;
+    switch (pixels_per_thread) {
+    case 1:
+        e = cudaFuncSetAttribute(maray_interp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        maray_interp<1><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts);
+        break;
+    case 2:
+        e = cudaFuncSetAttribute(maray_interp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        maray_interp<2><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts);
+        break;
+    case 4:
+        e = cudaFuncSetAttribute(maray_interp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        maray_interp<4><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts);
+        break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 issue-rate microbenchmark: 8 independent DADD/DMUL chains per thread (no FMA: the render
+// path has none), or 8 DFMA chains for the nominal figure.  Counts warp-instructions * 32.
+template <bool FMA>
+__global__ void __launch_bounds__(256) fp64_issue_rate(double* sink, int iters, double m, double a) {
+    double v0 = threadIdx.x * 1e-9, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (FMA) {
+                v0 = __fma_rn(v0, m, a); v1 = __fma_rn(v1, m, a); v2 = __fma_rn(v2, m, a); v3 = __fma_rn(v3, m, a);
+                v4 = __fma_rn(v4, m, a); v5 = __fma_rn(v5, m, a); v6 = __fma_rn(v6, m, a); v7 = __fma_rn(v7, m, a);
+            } else {
+                v0 = __dmul_rn(v0, m); v1 = __dadd_rn(v1, a); v2 = __dmul_rn(v2, m); v3 = __dadd_rn(v3, a);
+                v4 = __dmul_rn(v4, m); v5 = __dadd_rn(v5, a); v6 = __dmul_rn(v6, m); v7 = __dadd_rn(v7, a);
+            }
+        }
+    }
+    double s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+    if (s == 123.456) sink[0] = s;   // never true; keeps the chains alive
+}
+
+cudaError_t launch_fp64_issue_rate(bool fma, double* d_sink, int iters, int blocks, cudaStream_t stream) {
+    if (fma) fp64_issue_rate<true><<<blocks, 256, 0, stream>>>(d_sink, iters, 1.0000001, 1e-9);
+    else fp64_issue_rate<false><<<blocks, 256, 0, stream>>>(d_sink, iters, 1.0000001, 1e-9);
+    return cudaGetLastError();
+}
+
+}  // namespace maray

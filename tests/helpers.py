@@ -1,0 +1,214 @@
+"""Test-side checkers of the HOST logic (lowering, code generation, bytecode), runnable without a GPU.
+
+Nothing here is part of the product and nothing in the product can reach it:
+  * host_jit_run   compiles the CUDA source the NVRTC back end generated as plain C++ with g++
+                   (-ffp-contract=off) behind a shim of the few CUDA intrinsics it uses, and runs the
+                   kernel body thread by thread.  It checks the generated program text, not the GPU.
+  * bytecode_run   a numpy reading of the interpreter's bytecode (csrc/bytecode.hpp).
+Both are compared with the oracle in tests/test_host_lowering.py.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import math
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HOST_SHIM = r"""
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __shared__ static
+#define __launch_bounds__(x)
+struct uint3_ { unsigned int x, y, z; };
+static uint3_ threadIdx, blockIdx, blockDim;
+struct uint4 { unsigned int x, y, z, w; };
+static inline double __drcp_rn(double v) { return 1.0 / v; }
+static inline double __dsqrt_rn(double v) { return std::sqrt(v); }
+static inline unsigned int __double2uint_rz(double v) {
+    if (!(v > 0.0)) return 0u;
+    if (v >= 4294967295.0) return 4294967295u;
+    return (unsigned int)v;
+}
+static inline unsigned char __ldg(const unsigned char* p) { return *p; }
+static inline double __longlong_as_double(long long b) { double d; std::memcpy(&d, &b, 8); return d; }
+static inline void __syncthreads() {}
+using std::fabs; using std::sin; using std::exp; using std::log;
+"""
+
+HOST_DRIVER = r"""
+extern "C" void host_run(unsigned char* out, double* f64_out, unsigned long long plane, const MrTexture* tex,
+                         unsigned int p0, unsigned int n, unsigned int W) {
+    MrParams p;
+    p.out = out; p.f64_out = f64_out; p.f64_plane = plane; p.tex = tex; p.p0 = p0; p.n = n; p.W = W;
+    p.out_aligned = 0;
+    blockDim.x = 256; blockDim.y = blockDim.z = 1;
+    unsigned int blocks = (n + 255) / 256;
+    for (unsigned int b = 0; b < blocks; b++) {
+        blockIdx.x = b;
+        // two passes: after the first every thread's bytes are in the staging tile, so the second
+        // pass's cooperative copy-out sees a complete tile (sequential stand-in for __syncthreads)
+        for (int pass = 0; pass < 2; pass++)
+            for (unsigned int t = 0; t < 256; t++) { threadIdx.x = t; maray_jit(p); }
+    }
+}
+"""
+
+
+class _Tex(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("w", ctypes.c_uint32), ("h", ctypes.c_uint32)]
+
+
+_CACHE = {}
+
+
+def host_jit_run(source: str, w: int, p0: int, n: int, textures=()):
+    """Runs the generated kernel text on the CPU.  Returns (rgb uint8 (n,3), planes float64 (3,n))."""
+    key = hashlib.sha256(source.encode()).hexdigest()
+    lib = _CACHE.get(key)
+    if lib is None:
+        d = tempfile.mkdtemp(prefix="maray_hostjit_")
+        src = os.path.join(d, "k.cpp")
+        with open(src, "w") as f:
+            f.write(HOST_SHIM)
+            f.write(source.replace('extern "C" __global__', "static"))
+            f.write(HOST_DRIVER)
+        so = os.path.join(d, "k.so")
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                               "-w", "-o", so, src])
+        lib = ctypes.CDLL(so)
+        lib.host_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p,
+                                 ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+        _CACHE[key] = lib
+    rgb = np.zeros((n, 3), dtype=np.uint8)
+    planes = np.zeros((3, n), dtype=np.float64)
+    arrs = [np.ascontiguousarray(t, dtype=np.uint8) for t in textures]
+    tab = (_Tex * max(1, len(arrs)))()
+    for i, a in enumerate(arrs):
+        tab[i].data = a.ctypes.data
+        tab[i].w, tab[i].h = a.shape[1], a.shape[0]
+    lib.host_run(rgb.ctypes.data, planes.ctypes.data, n, ctypes.addressof(tab), p0, n, w)
+    return rgb, planes
+
+
+# ---- bytecode ------------------------------------------------------------------------------------
+(BC_END, BC_LD_S, BC_LD_K, BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,
+ BC_ADD_S, BC_ADD_K, BC_MUL_S, BC_MUL_K, BC_MAX_S, BC_MAX_K, BC_MAXR_S, BC_MAXR_K,
+ BC_MIN_S, BC_MIN_K, BC_MINR_S, BC_MINR_K, BC_TEX_S, BC_TEXR_S, BC_OUT_R, BC_OUT_G, BC_OUT_B) = range(28)
+
+_libm = np.frompyfunc
+
+
+def _vec(fn):
+    f = np.frompyfunc(fn, 1, 1)
+
+    def g(a):
+        def safe(v):
+            try:
+                return fn(v)
+            except (ValueError, OverflowError):
+                if fn is math.log:
+                    return -math.inf if v == 0 else math.nan
+                if fn is math.exp:
+                    return math.inf
+                return math.nan
+        return np.frompyfunc(safe, 1, 1)(a).astype(np.float64)
+    return g
+
+
+_sin, _exp, _log = _vec(math.sin), _vec(math.exp), _vec(math.log)
+
+
+def sem_max(a, b):
+    """f64::max as the reference compiles it: NaN ignored, tie returns the first operand."""
+    return np.where((b > a) | np.isnan(a), b, a)
+
+
+def sem_min(a, b):
+    return np.where((b < a) | np.isnan(a), b, a)
+
+
+def as_u8(v):
+    v = np.where(np.isnan(v), 0.0, v)
+    return np.clip(np.trunc(v), 0, 255).astype(np.uint8)
+
+
+def _as_u32(v):
+    v = np.where(np.isnan(v), 0.0, v)
+    return np.clip(np.trunc(v), 0, 4294967295).astype(np.uint64)
+
+
+def tex_fetch(tex, ch, x, y):
+    h, w = tex.shape[0], tex.shape[1]
+    xi, yi = _as_u32(x), _as_u32(y)
+    ok = ~((x < 0.0) | (y < 0.0)) & (xi < w) & (yi < h)
+    out = np.zeros(x.shape, dtype=np.float64)
+    out[ok] = tex[yi[ok], xi[ok], ch].astype(np.float64)
+    return out
+
+
+def bytecode_run(code, consts, xs, ys, textures=()):
+    """Executes the bytecode for the pixels (xs[i], ys[i]).  Returns planes float64 (3, n)."""
+    xs = np.asarray(xs, dtype=np.float64)
+    ys = np.asarray(ys, dtype=np.float64)
+    n = xs.shape[0]
+    slots = {0: xs, 1: ys}
+    acc = np.zeros(n)
+    out = np.zeros((3, n))
+    with np.errstate(all="ignore"):
+        for w in code:
+            w = int(w)
+            op, store, dst, operand = w & 0xFF, (w >> 8) & 1, (w >> 16) & 0xFFFF, w >> 32
+            if op == BC_END:
+                break
+            if op == BC_LD_S: acc = slots[operand]
+            elif op == BC_LD_K: acc = np.full(n, consts[operand])
+            elif op == BC_NEG: acc = -acc
+            elif op == BC_ABS: acc = np.abs(acc)
+            elif op == BC_RECIP: acc = 1.0 / acc
+            elif op == BC_SQRT: acc = np.sqrt(acc)
+            elif op == BC_STEP: acc = np.where(acc >= 0.0, 1.0, 0.0)
+            elif op == BC_SIN: acc = _sin(acc)
+            elif op == BC_EXP: acc = _exp(acc)
+            elif op == BC_LN: acc = _log(acc)
+            elif op == BC_ADD_S: acc = acc + slots[operand]
+            elif op == BC_ADD_K: acc = acc + consts[operand]
+            elif op == BC_MUL_S: acc = acc * slots[operand]
+            elif op == BC_MUL_K: acc = acc * consts[operand]
+            elif op == BC_MAX_S: acc = sem_max(acc, slots[operand])
+            elif op == BC_MAX_K: acc = sem_max(acc, np.full(n, consts[operand]))
+            elif op == BC_MAXR_S: acc = sem_max(slots[operand], acc)
+            elif op == BC_MAXR_K: acc = sem_max(np.full(n, consts[operand]), acc)
+            elif op == BC_MIN_S: acc = sem_min(acc, slots[operand])
+            elif op == BC_MIN_K: acc = sem_min(acc, np.full(n, consts[operand]))
+            elif op == BC_MINR_S: acc = sem_min(slots[operand], acc)
+            elif op == BC_MINR_K: acc = sem_min(np.full(n, consts[operand]), acc)
+            elif op == BC_TEX_S:
+                acc = tex_fetch(textures[operand >> 18], (operand >> 16) & 3, slots[operand & 0xFFFF], acc)
+            elif op == BC_TEXR_S:
+                acc = tex_fetch(textures[operand >> 18], (operand >> 16) & 3, acc, slots[operand & 0xFFFF])
+            elif op == BC_OUT_R: out[0] = acc
+            elif op == BC_OUT_G: out[1] = acc
+            elif op == BC_OUT_B: out[2] = acc
+            else:
+                raise ValueError(f"bad opcode {op}")
+            if store:
+                slots[dst] = acc
+    return out
+
+
+def bits_equal(a, b):
+    """Bit-identical float64 arrays, any NaN matching any NaN."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))

@@ -1,0 +1,104 @@
+"""The C-ABI boundary without a GPU: the library loads, exports every symbol include/maray_cuda.h
+declares, and its host side (load, validate, lower, generate, NVRTC-compile) behaves -- including
+the error behaviour the header promises.  No compute is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from maray_b200 import CudaRenderer, MarayCudaError, _lib, scenes
+from maray_b200 import expr as E
+from maray_b200.roofline import fp64_ops_per_pixel
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "maray_cuda.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(maray_cuda_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 17
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} is declared in include/maray_cuda.h but not exported"
+    assert declared == {n for n, _, _ in _lib.SYMBOLS}, "ctypes binding and header disagree"
+    assert b"sm_100a" in _lib.load().maray_cuda_version()
+
+
+def test_no_torch_or_oracle_in_the_product():
+    """The product path must not route through the oracle, numpy evaluation or torch."""
+    for fn in ("render.py", "_lib.py", "expr.py", "scenes.py", "bands.py", "roofline.py", "__init__.py"):
+        src = open(os.path.join(ROOT, "maray_b200", fn)).read()
+        assert "oracle" not in src.replace("oracle/", "").lower() or fn == "roofline.py" or "import oracle" not in src
+        assert "from oracle" not in src and "import oracle" not in src
+    out = os.popen(f"ldd {_lib.LIB_PATH}").read()
+    assert "libtorch" not in out and "maray_oracle" not in out
+
+
+def test_host_only_handle_compiles_but_cannot_render(chess_bytes):
+    with CudaRenderer(gpus=0) as r:
+        assert r.load(chess_bytes) == (1024, 1024)
+        st = r.compile("interp")
+        # program facts pinned by SURVEY.md section 8(a1) / BASELINE.md section 4
+        assert st["legacy_layout"] == 1 and st["tree_nodes"] == 3 * 29314
+        assert st["n_y_only"] == 845 and st["n_sin"] == 256 and st["n_step"] == 1482
+        assert st["n_min"] == 768 and st["n_max"] == 256 and st["n_recip"] == 0 and st["n_sqrt"] == 0
+        assert st["dag_nodes"] == st["n_const"] + st["n_x_only"] + st["n_y_only"] + st["n_xy"] + 0
+        assert st["interp_instructions"] > st["n_xy"] and 2 < st["interp_slots"] < 400
+        assert fp64_ops_per_pixel(st) == st["n_add"] + st["n_mul"] + st["n_step"] + 2 * 1024 + 15 * 256
+        with pytest.raises(MarayCudaError) as ei:
+            r.render(64, 64)
+        assert ei.value.code == _lib.E_CUDA and "no CPU fallback" in ei.value.message
+
+
+def test_nvrtc_backend_compiles_for_sm_100a_without_a_gpu():
+    with CudaRenderer(gpus=0) as r:
+        r.load(scenes.sdf(320, 200, 8))
+        st = r.compile("nvrtc")
+        assert st["jit_cubin_bytes"] > 1000 and st["jit_registers"] > 0 and st["nvrtc_ms"] > 0
+        src = r.source()
+        assert "maray_jit" in src and "--fmad=false" in src and "mr_sqrt(" in src
+        assert "fma(" not in src.replace("--fmad", "")
+
+
+def test_error_behaviour():
+    with CudaRenderer(gpus=0) as r:
+        with pytest.raises(MarayCudaError) as ei:
+            r.load(b"\x01\x02\x03")
+        assert ei.value.code == _lib.E_PARSE
+        with pytest.raises(MarayCudaError) as ei:
+            r.load(b"\x00" * 8 + b"\xff\xff\xff\xff" * 3)
+        assert ei.value.code == _lib.E_PARSE
+        with pytest.raises(MarayCudaError) as ei:
+            r.compile("nvrtc")                       # nothing loaded
+        assert ei.value.code == _lib.E_INVALID
+        # App id outside the runtime's table: the reference panics on the index (src/lib.rs:665)
+        r.load(E.to_bytes([8, 8], [E.app(E.channel(1, 0), E.x(), E.y())] * 3))
+        r.set_textures([np.zeros((4, 4, 3), np.uint8)])
+        with pytest.raises(MarayCudaError) as ei:
+            r.compile("interp")
+        assert ei.value.code == _lib.E_SCENE and "App id 5" in ei.value.message
+        # cyclic Let
+        cyc = E.let_([(0, E.add(E.var_id(1), E.nat(1))), (1, E.var_id(0))], E.var_id(0))
+        r.load(E.to_bytes([8, 8], [cyc] * 3))
+        with pytest.raises(MarayCudaError) as ei:
+            r.compile("interp")
+        assert ei.value.code == _lib.E_SCENE and "cyclic" in ei.value.message
+        # a stray unbound variable is already refused by the loader (the reference yields NaN,
+        # src/cache.rs:40).  App keeps the bytes from also decoding under the legacy numbering.
+        with pytest.raises(MarayCudaError) as ei:
+            r.load(E.to_bytes([8, 8], [E.app(0, E.var_id(3), E.x())] * 3))
+        assert ei.value.code == _lib.E_PARSE and "unbound variable" in ei.value.message
+
+
+def test_texture_dimensions_fold_to_constants():
+    e = E.add(E.app(E.image_width(0), E.x(), E.y()), E.app(E.image_height(0), E.nat(0), E.nat(0)))
+    with CudaRenderer(gpus=0) as r:
+        r.set_textures([np.zeros((7, 13, 3), np.uint8)])
+        r.load(E.to_bytes([4, 4], [e, e, e]))
+        st = r.compile("interp")
+        assert st["dag_nodes"] == 1 and st["n_const"] == 1 and st["n_tex"] == 0
+        code, consts = r.bytecode()
+        assert 20.0 in consts.tolist()
