@@ -49,38 +49,51 @@ def parse_args():
 
 
 # ---- CPU arm: the reference's algorithm (oracle port) on the host cores ---------------------------
+def host_threads() -> int:
+    """Threads the CPU arm may use: the affinity mask, capped by a cgroup CPU quota if one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_render_sample(scene_bytes, textures, w, h, target_s, threads):
     """Times the oracle (restatement of par_gen_to_image, all host threads) on a bounded sample of the
-    workload: evenly spaced full rows, count chosen from a one-row probe so the run lasts ~target_s."""
+    workload: batches of evenly spread full rows (one row per thread per batch) until ~target_s of
+    wall time is used.  Scenes so expensive that one row would blow the budget are sampled as
+    short row segments instead.  Returns (Mpixel/s, seconds, description)."""
     from oracle.oracle import OracleScene
 
     sc = OracleScene(scene_bytes, textures)
-    probe_w = min(w, 256)
+    probe = min(w, 32)
     t0 = time.perf_counter()
-    sc.render_window(0, probe_w, h // 2, h // 2 + 1, threads=1)
-    per_px_1t = (time.perf_counter() - t0) / probe_w
-    px_budget = target_s * threads / max(per_px_1t, 1e-9)
-    rows = int(px_budget // w)
-    if rows >= threads:
-        rows = min(h, rows)
-        ys = sorted({int((i + 0.5) * h / rows) for i in range(rows)})
-        t0 = time.perf_counter()
-        sc.render_rows(ys, w, threads=threads) if len(ys) != h else sc.render(w, h, threads)
+    sc.render_window(0, probe, h // 2, h // 2 + 1, threads=1)
+    per_px = (time.perf_counter() - t0) / probe            # one thread, one mid-frame pixel
+    seg = w if per_px * w <= target_s / 2 else max(1, min(w, int(target_s / 2 / per_px)))
+    npx, batches = 0, 0
+    t0 = time.perf_counter()
+    while True:
+        # rows spread over the frame, different every batch
+        ys = sorted({int(((i + 0.5) / threads + batches * 0.6180339887) % 1.0 * h) for i in range(threads)})
+        if seg == w:
+            sc.render_rows(ys, w, threads=threads)
+        else:
+            # `threads` consecutive rows so every thread pulls one row segment
+            y0 = min(max(0, ys[len(ys) // 2]), max(0, h - threads))
+            sc.render_window(0, seg, y0, min(h, y0 + threads), threads=threads)
+            ys = list(range(y0, min(h, y0 + threads)))
+        npx += len(ys) * seg
+        batches += 1
         dt = time.perf_counter() - t0
-        npx = len(ys) * w
-        sample = f"{len(ys)} evenly spaced full rows of the {w}x{h} frame ({npx} pixels)"
-    else:
-        # very expensive scenes: one short row segment per thread
-        seg = max(1, int(px_budget // threads))
-        seg = min(seg, w)
-        t0 = time.perf_counter()
-        # `threads` rows of `seg` pixels: each thread pulls one row
-        ys0 = max(0, h // 2 - threads // 2)
-        sc.render_window(0, seg, ys0, min(h, ys0 + threads), threads=threads)
-        dt = time.perf_counter() - t0
-        npx = seg * (min(h, ys0 + threads) - ys0)
-        sample = f"{npx} pixels ({seg}-pixel segments of {min(h, ys0 + threads) - ys0} mid-frame rows) of the {w}x{h} frame"
+        if dt >= target_s or dt + dt / batches > 1.5 * target_s or npx >= w * h:
+            break
     sc.close()
+    what = "full rows" if seg == w else f"{seg}-pixel row segments"
+    sample = f"{npx} pixels of the {w}x{h} frame ({batches} batches of {threads} {what} spread over the frame)"
     return npx / dt / 1e6, dt, sample
 
 
@@ -94,7 +107,7 @@ def run_reference(args):
     from maray_b200 import scenes
 
     scene_bytes, textures, (w, h) = scenes.by_name(args.workload)
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     per_step_s = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     vals = []
     sample = ""
@@ -118,8 +131,8 @@ def run_reference(args):
 
 # ---- clocks ---------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and clock-event (throttle) reasons of one GPU during the timed region, through
+    NVML (a few ms per sample; nvidia-smi takes longer than a short timed region lasts)."""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
@@ -130,21 +143,36 @@ class ClockSampler:
         self._th = None
 
     def _run(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
-                parts = [p.strip() for p in out.split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(float(parts[0]))
-                    self.max_mhz = float(parts[1])
-                    for n, v in zip(names, parts[2:6]):
-                        if v.lower().startswith("active"):
-                            self.reasons.add(n)
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            hnd = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(hnd, nv.NVML_CLOCK_SM))
+            bits = {
+                "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            }
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(hnd, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
+                    for name, bit in bits.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                self._stop.wait(0.01)
+        except Exception as exc:   # NVML unavailable: say so instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
 
     def start(self):
         self._th = threading.Thread(target=self._run, daemon=True)
@@ -297,7 +325,7 @@ def run_ours(args):
                         "interp_instructions": stats["interp_instructions"], "interp_slots": stats["interp_slots"]},
         }
         if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
             v, dt, sample = cpu_render_sample(scene_bytes, textures, w, h, args.cpu_sample_s, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                                     "seconds": dt}

@@ -73,6 +73,8 @@ struct maray_cuda {
     std::vector<char> cubin;
     Bytecode bc;
     unsigned interp_block = 128, interp_ppt = 2;
+    unsigned jit_block = 256;
+    unsigned jit_maxreg = 0;
     maray_cuda_stats stats{};
     int report_kind = MARAY_REPORT_NONE;
     uint32_t report_every = 0;
@@ -166,14 +168,16 @@ int nvrtc_compile(maray_cuda* h) {
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, h->source.c_str(), "maray_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
         return fail(h, MARAY_E_COMPILE, "nvrtcCreateProgram failed");
-    const char* opts[] = {
+    std::vector<const char*> opts = {
         "--gpu-architecture=sm_100a",
         "--fmad=false",               // the reference never fuses a*b+c
         "--std=c++17",
         "-lineinfo",
         "--ptxas-options=-v",
     };
-    nvrtcResult rc = nvrtcCompileProgram(prog, int(sizeof opts / sizeof opts[0]), opts);
+    std::string maxreg = "--maxrregcount=" + std::to_string(h->jit_maxreg);
+    if (h->jit_maxreg) opts.push_back(maxreg.c_str());
+    nvrtcResult rc = nvrtcCompileProgram(prog, int(opts.size()), opts.data());
     size_t log_size = 0;
     nvrtcGetProgramLogSize(prog, &log_size);
     std::string log(log_size, '\0');
@@ -191,13 +195,15 @@ int nvrtc_compile(maray_cuda* h) {
     h->cubin.resize(cubin_size);
     nvrtcGetCUBIN(prog, h->cubin.data());
     nvrtcDestroyProgram(&prog);
-    // registers of the kernel from the ptxas -v log: "... Function properties for maray_jit ... Used N registers"
+    // registers of the kernel from the ptxas -v log:
+    //   "Function properties for maray_jit" ... "Used N registers"
     h->stats.jit_registers = 0;
-    size_t at = log.find(std::string("Compiling entry function '") + kJitKernelName + "'");
+    size_t at = log.find(std::string("Function properties for ") + kJitKernelName);
     if (at != std::string::npos) {
         size_t u = log.find("Used ", at);
         if (u != std::string::npos) h->stats.jit_registers = uint32_t(std::atoi(log.c_str() + u + 5));
     }
+    if (std::getenv("MARAY_JIT_VERBOSE")) std::fprintf(stderr, "%s\n", log.c_str());
     return MARAY_OK;
 }
 
@@ -223,8 +229,8 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
     if (n == 0) return MARAY_OK;
     if (h->backend == MARAY_BACKEND_NVRTC) {
         void* args[] = {&p};
-        unsigned grid = (n + kJitBlock - 1) / kJitBlock;
-        CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(kJitBlock), args, 0, stream));
+        unsigned grid = (n + h->jit_block - 1) / h->jit_block;
+        CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, 0, stream));
     } else {
         CU_TRY(h, launch_interp(p, g.d_code, unsigned(h->bc.code.size()), g.d_consts, h->bc.n_slots, h->interp_block,
                                 h->interp_ppt, stream));
@@ -459,8 +465,13 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         // tuning knobs (documented in DESIGN.md "NVRTC back end")
         if (const char* e = std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_INLINE_TRANS_BELOW")) copt.inline_transcendentals_below = uint32_t(std::strtoul(e, nullptr, 10));
+        if (const char* e = std::getenv("MARAY_JIT_BLOCK")) copt.block = uint32_t(std::strtoul(e, nullptr, 10));
+        if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10));
+        h->jit_maxreg = 0;
+        if (const char* e = std::getenv("MARAY_JIT_MAXREG")) h->jit_maxreg = unsigned(std::strtoul(e, nullptr, 10));
         h->source = generate_cuda_source(h->prog, copt, &info);
         h->stats.codegen_ms = now_ms() - t1;
+        h->jit_block = info.block;
         h->stats.jit_segments = info.segments;
         h->stats.jit_frame_slots = info.frame_slots;
         h->stats.jit_source_bytes = uint32_t(h->source.size());

@@ -13,22 +13,26 @@ struct CodegenOptions {
     // Programs with more values than this are cut into __noinline__ device functions of this many
     // values each; values that cross a cut live in a per-thread frame (local memory).  Bounds
     // ptxas time, which is super-linear in basic-block size.
-    uint32_t segment_values = 4096;
+    uint32_t segment_values = 32768;
     // sin/exp/ln are inlined below this many transcendental values, called out-of-line above it
     // (their inlined bodies dominate code size and compile time in transcendental-heavy scenes).
     uint32_t inline_transcendentals_below = 2048;
+    // Threads per block of the generated kernel (a multiple of 32; one pixel per thread).
+    uint32_t block = 256;
+    // __launch_bounds__ second argument: resident blocks per SM the register allocation must allow
+    // (0 = leave it to ptxas).
+    uint32_t min_blocks_per_sm = 0;
 };
 
 struct CodegenInfo {
     uint32_t segments = 0;
     uint32_t frame_slots = 0;       // doubles of per-thread frame (0 when not segmented)
     bool transcendentals_inlined = true;
+    uint32_t block = 256;           // threads per block the kernel must be launched with
 };
 
 // Name of the generated kernel (extern "C").
 extern const char* const kJitKernelName;
-// Threads per block the generated kernel is written for.
-constexpr unsigned kJitBlock = 256;
 
 std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt, CodegenInfo* info);
 

@@ -681,9 +681,10 @@ double mo_eval(const mo_scene *s, int channel, double x, double y) {
  * values, 3 planes of (y1-y0)*(x1-x0) doubles.                                                */
 typedef struct {
     const mo_scene *s;
-    uint32_t x0, x1, y0, y1;
+    uint32_t x0, x1;
+    const uint32_t *rows; uint32_t n_rows;      /* image rows to render; output row i = rows[i] */
     uint8_t *rgb; double *planes;
-    pthread_mutex_t mu; uint32_t next_row;
+    pthread_mutex_t mu; uint32_t next;          /* shared row counter (reference src/render.rs:150) */
     int fault;
 } RenderJob;
 
@@ -692,14 +693,15 @@ static void *render_thread(void *arg) {
     const mo_scene *s = j->s;
     Rt rt = {&s->tex, s->tex.n * ALIGN, 0};
     Cache cache; cache_init(&cache);
-    uint32_t ww = j->x1 - j->x0, hh = j->y1 - j->y0;
+    uint32_t ww = j->x1 - j->x0, hh = j->n_rows;
     size_t plane = (size_t)ww * hh;
     for (;;) {
         pthread_mutex_lock(&j->mu);
-        uint32_t y = j->next_row;
-        if (y < j->y1) j->next_row++;
+        uint32_t i = j->next;
+        if (i < j->n_rows) j->next++;
         pthread_mutex_unlock(&j->mu);
-        if (y >= j->y1) break;
+        if (i >= j->n_rows) break;
+        uint32_t y = j->rows[i];
         cache_clear(&cache);                                         /* fresh Cache per row */
         for (uint32_t x = j->x0; x < j->x1; x++) {
             cache_clear_dep_x(&cache);
@@ -707,7 +709,7 @@ static void *render_thread(void *arg) {
             double r = eval2(s->color[0], &rt, p, &EMPTY_CTX, &cache);
             double g = eval2(s->color[1], &rt, p, &EMPTY_CTX, &cache);
             double b = eval2(s->color[2], &rt, p, &EMPTY_CTX, &cache);
-            size_t o = (size_t)(y - j->y0) * ww + (x - j->x0);
+            size_t o = (size_t)i * ww + (x - j->x0);
             if (j->rgb) {
                 j->rgb[o * 3 + 0] = f64_as_u8(r);
                 j->rgb[o * 3 + 1] = f64_as_u8(g);
@@ -723,16 +725,17 @@ static void *render_thread(void *arg) {
     return NULL;
 }
 
-/* Returns 0, or -1 when the reference would have panicked (App id outside Runtime::functions). */
-int mo_render_window(const mo_scene *s, uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
-                     int nthreads, uint8_t *rgb, double *f64_planes) {
-    if (x1 < x0 || y1 < y0) return -2;
+/* Renders the listed rows (any order, any subset) of columns [x0,x1).
+ * Returns 0, or -1 when the reference would have panicked (App id outside Runtime::functions). */
+int mo_render_rows(const mo_scene *s, uint32_t x0, uint32_t x1, const uint32_t *rows, uint32_t n_rows,
+                   int nthreads, uint8_t *rgb, double *f64_planes) {
+    if (x1 < x0) return -2;
+    if (n_rows == 0 || x1 == x0) return 0;
     RenderJob j; memset(&j, 0, sizeof j);
-    j.s = s; j.x0 = x0; j.x1 = x1; j.y0 = y0; j.y1 = y1; j.rgb = rgb; j.planes = f64_planes;
-    j.next_row = y0;
+    j.s = s; j.x0 = x0; j.x1 = x1; j.rows = rows; j.n_rows = n_rows; j.rgb = rgb; j.planes = f64_planes;
     pthread_mutex_init(&j.mu, NULL);
     if (nthreads < 1) nthreads = 1;
-    if ((uint32_t)nthreads > y1 - y0 && y1 > y0) nthreads = (int)(y1 - y0);
+    if ((uint32_t)nthreads > n_rows) nthreads = (int)n_rows;
     pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
     int started = 0;
     for (int i = 0; i < nthreads; i++) if (!run_big_stack(render_thread, &j, &th[started])) started++;
@@ -741,6 +744,17 @@ int mo_render_window(const mo_scene *s, uint32_t x0, uint32_t x1, uint32_t y0, u
     pthread_mutex_destroy(&j.mu);
     if (!started) return -3;
     return j.fault ? -1 : 0;
+}
+
+int mo_render_window(const mo_scene *s, uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                     int nthreads, uint8_t *rgb, double *f64_planes) {
+    if (x1 < x0 || y1 < y0) return -2;
+    uint32_t n = y1 - y0;
+    uint32_t *rows = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+    for (uint32_t i = 0; i < n; i++) rows[i] = y0 + i;
+    int rc = mo_render_rows(s, x0, x1, rows, n, nthreads, rgb, f64_planes);
+    free(rows);
+    return rc;
 }
 
 /* Whole image of size w x h (gen_to_image with an RgbImage of that size, src/lib.rs:1177-1195). */

@@ -43,6 +43,8 @@ def lib():
         L.mo_eval.restype = ctypes.c_double
         L.mo_eval.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]
         L.mo_render_window.argtypes = [ctypes.c_void_p] + [ctypes.c_uint32] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.mo_render_rows.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32,
+                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.mo_render.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
         _lib = L
     return _lib
@@ -103,18 +105,17 @@ class OracleScene:
         return self.render_window(0, w, 0, h, threads)
 
     def render_rows(self, rows: Sequence[int], w: Optional[int] = None, threads: int = 0) -> np.ndarray:
-        """RGB8 (len(rows), w, 3): full rows `rows` of the image."""
+        """RGB8 (len(rows), w, 3): full rows `rows` of the image (any subset, any order); the rows are
+        the work items the threads pull, as in the reference's row scheduling."""
         w = self.size[0] if w is None else w
-        out = np.zeros((len(rows), w, 3), dtype=np.uint8)
-        # consecutive runs are rendered in one call so threads have several rows to pull
-        i = 0
-        rows = list(rows)
-        while i < len(rows):
-            j = i
-            while j + 1 < len(rows) and rows[j + 1] == rows[j] + 1:
-                j += 1
-            out[i:j + 1] = self.render_window(0, w, rows[i], rows[j] + 1, threads)
-            i = j + 1
+        threads = threads or (os.cpu_count() or 1)
+        rows_a = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.zeros((len(rows_a), w, 3), dtype=np.uint8)
+        rc = lib().mo_render_rows(self._h, 0, w, rows_a.ctypes.data, len(rows_a), threads, out.ctypes.data, None)
+        if rc == -1:
+            raise IndexError("oracle: App id outside Runtime::functions (the reference panics here)")
+        if rc != 0:
+            raise RuntimeError(f"oracle: render failed ({rc})")
         return out
 
     def close(self) -> None:

@@ -135,7 +135,23 @@ def test_textured_scene(backend):
     want_rows = oracle.render_rows(rows, 960)
     for i, y in enumerate(rows):
         assert np.array_equal(frame[y], want_rows[i])
-    assert (frame == 0).all(axis=2).any() and (frame != 0).any()      # both branches were exercised
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_texture_edges_and_out_of_range(backend):
+    """fun_color_channel's early returns (reference src/textures.rs:30,34): negative coordinates,
+    coordinates at and beyond the texture edge, and the truncation of fractional coordinates."""
+    tex = scenes.synthetic_textures(2, 16)
+    x, y = E.x(), E.y()
+    u = E.div(E.sub(x, E.nat(6)), E.nat(2))          # -3.0 .. 12.5 in steps of .5
+    v = E.sub(y, E.nat(3))
+    color = [E.app(E.channel(0, 0), u, v), E.app(E.channel(1, 1), v, u), E.app(E.channel(1, 2), u, E.mul(v, v))]
+    scene = E.to_bytes([40, 24], color)
+    want_rgb, want = OracleScene(scene, tex).render_window(0, 40, 0, 24, want_f64=True)
+    with _renderer(scene, backend, tex) as r:
+        planes, rgb = r.render_window_f64(40, 24, 0, 40, 0, 24)
+    assert bits_equal(planes, want).all() and np.array_equal(rgb, want_rgb)
+    assert (want[0][:, :6] == 0).all() and (want[0][:3] == 0).all() and (want[0][3:19, 6:38] != 0).any()
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
