@@ -24,10 +24,15 @@ __device__ __forceinline__ double mr_recip(double v) { return __drcp_rn(v); }
 __device__ __forceinline__ double mr_sqrt(double v) { return __dsqrt_rn(v); }
 
 // `f64 as u8`: truncate toward zero, saturate to [0,255], NaN -> 0.  reference src/render.rs:26-28
-// cvt.rzi.u32.f64 saturates and maps NaN to 0; the upper clamp finishes the job.
+// fmax(v, 0) maps NaN and negatives to 0 (CUDA fmax returns the non-NaN operand), fmin clamps the
+// top; the conversion then only ever sees [0, 255].  (The conversion is NOT relied on for NaN:
+// measured on sm_100a, cvt.rzi.u32.f64 of the NaN produced by inf*0 is not 0.)
 __device__ __forceinline__ unsigned int mr_as_u8(double v) {
-    unsigned int u = __double2uint_rz(v);
-    return u > 255u ? 255u : u;
+    return __double2uint_rz(fmin(fmax(v, 0.0), 255.0));
+}
+// `f64 as u32` for a value already known not to be negative: saturating, NaN -> 0.
+__device__ __forceinline__ unsigned int mr_as_u32_nonneg(double v) {
+    return __double2uint_rz(fmax(v, 0.0));
 }
 
 // fun_color_channel.  reference src/textures.rs:27-36
@@ -36,8 +41,8 @@ __device__ __forceinline__ unsigned int mr_as_u8(double v) {
 __device__ __forceinline__ double mr_tex(const unsigned char* __restrict__ data, unsigned int w, unsigned int h,
                                          unsigned int k, double x, double y) {
     if (x < 0.0 || y < 0.0) return 0.0;
-    unsigned int xi = __double2uint_rz(x);
-    unsigned int yi = __double2uint_rz(y);
+    unsigned int xi = mr_as_u32_nonneg(x);
+    unsigned int yi = mr_as_u32_nonneg(y);
     if (xi >= w || yi >= h) return 0.0;
     return (double)__ldg(data + ((size_t)yi * w + xi) * 3u + k);
 }

@@ -36,6 +36,7 @@ struct uint4 { unsigned int x, y, z, w; };
 static inline double __drcp_rn(double v) { return 1.0 / v; }
 static inline double __dsqrt_rn(double v) { return std::sqrt(v); }
 static inline unsigned int __double2uint_rz(double v) {
+    if (v != v) return 0xffffffffu;   // pessimistic: generated code must not rely on NaN -> 0
     if (!(v > 0.0)) return 0u;
     if (v >= 4294967295.0) return 4294967295u;
     return (unsigned int)v;
@@ -43,7 +44,7 @@ static inline unsigned int __double2uint_rz(double v) {
 static inline unsigned char __ldg(const unsigned char* p) { return *p; }
 static inline double __longlong_as_double(long long b) { double d; std::memcpy(&d, &b, 8); return d; }
 static inline void __syncthreads() {}
-using std::fabs; using std::sin; using std::exp; using std::log;
+using std::fabs; using std::sin; using std::exp; using std::log; using std::fmax; using std::fmin;
 """
 
 HOST_DRIVER = r"""

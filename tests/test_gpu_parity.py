@@ -145,7 +145,9 @@ def test_texture_edges_and_out_of_range(backend):
     x, y = E.x(), E.y()
     u = E.div(E.sub(x, E.nat(6)), E.nat(2))          # -3.0 .. 12.5 in steps of .5
     v = E.sub(y, E.nat(3))
-    color = [E.app(E.channel(0, 0), u, v), E.app(E.channel(1, 1), v, u), E.app(E.channel(1, 2), u, E.mul(v, v))]
+    nan_at_9 = E.mul(E.recip(E.nat(0)), E.sub(x, E.nat(9)))   # inf*(x-9): NaN at x == 9, +-inf elsewhere
+    color = [E.app(E.channel(0, 0), u, v), E.app(E.channel(1, 1), v, u),
+             E.app(E.channel(1, 2), E.min(u, nan_at_9), E.mul(v, v))]   # NaN coordinate -> texel column 0
     scene = E.to_bytes([40, 24], color)
     want_rgb, want = OracleScene(scene, tex).render_window(0, 40, 0, 24, want_f64=True)
     with _renderer(scene, backend, tex) as r:

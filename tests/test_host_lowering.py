@@ -85,7 +85,9 @@ def test_let_scoping_and_sharing():
     tex = scenes.synthetic_textures(1, 32)
     e = E.app(E.channel(0, 1), E.nat(5), y)
     e2 = E.app(E.channel(0, 2), x, E.nat(7))
-    _check_scene(E.to_bytes([16, 8], [e, e2, E.add(e, e2)]), 16, [0, 7], tex)
+    nan_at_9 = E.mul(E.recip(E.nat(0)), E.sub(x, E.nat(9)))            # NaN at x == 9
+    e3 = E.app(E.channel(0, 0), E.min(x, nan_at_9), y)                  # NaN coordinate -> column 0
+    _check_scene(E.to_bytes([16, 8], [e, e2, E.add(e3, e2)]), 16, [0, 7], tex)
 
 
 def test_nan_inf_and_zero_sign_semantics():
