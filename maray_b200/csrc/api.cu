@@ -465,6 +465,8 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         // tuning knobs (documented in DESIGN.md "NVRTC back end")
         if (const char* e = std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_INLINE_TRANS_BELOW")) copt.inline_transcendentals_below = uint32_t(std::strtoul(e, nullptr, 10));
+        if (const char* e = std::getenv("MARAY_JIT_SYNC_EVERY")) copt.sync_every = uint32_t(std::strtoul(e, nullptr, 10));
+        if (const char* e = std::getenv("MARAY_JIT_CONST_BANK")) copt.constants_in_bank = std::strtoul(e, nullptr, 10) != 0;
         if (const char* e = std::getenv("MARAY_JIT_BLOCK")) copt.block = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10));
         h->jit_maxreg = 0;
@@ -475,6 +477,8 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         h->stats.jit_segments = info.segments;
         h->stats.jit_frame_slots = info.frame_slots;
         h->stats.jit_source_bytes = uint32_t(h->source.size());
+        if (std::getenv("MARAY_JIT_SOURCE_ONLY"))   // tooling: inspect the generated text without paying for NVRTC
+            return fail(h, MARAY_E_COMPILE, "MARAY_JIT_SOURCE_ONLY is set: source generated, not compiled");
         double t2 = now_ms();
         int rc = nvrtc_compile(h);
         h->stats.nvrtc_ms = now_ms() - t2;

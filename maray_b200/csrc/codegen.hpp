@@ -13,15 +13,23 @@ struct CodegenOptions {
     // Programs with more values than this are cut into __noinline__ device functions of this many
     // values each; values that cross a cut live in a per-thread frame (local memory).  Bounds
     // ptxas time, which is super-linear in basic-block size.
-    uint32_t segment_values = 32768;
+    uint32_t segment_values = 16384;
     // sin/exp/ln are inlined below this many transcendental values, called out-of-line above it
     // (their inlined bodies dominate code size and compile time in transcendental-heavy scenes).
     uint32_t inline_transcendentals_below = 2048;
     // Threads per block of the generated kernel (a multiple of 32; one pixel per thread).
     uint32_t block = 256;
     // __launch_bounds__ second argument: resident blocks per SM the register allocation must allow
-    // (0 = leave it to ptxas).
-    uint32_t min_blocks_per_sm = 0;
+    // (0 = leave it to ptxas).  2 x 256 threads caps the kernel at 128 registers = 16 resident warps
+    // per SM, the best point of the sweep in profiles/ (ptxas left alone lands anywhere in 128..190).
+    uint32_t min_blocks_per_sm = 2;
+    // A block-wide barrier every this many statements (0 = none).  The kernel is hundreds of KB of
+    // straight-line code, far beyond the instruction caches; keeping the warps of a block within
+    // one cache's reach of each other lets them share instruction fetches.
+    uint32_t sync_every = 0;
+    // Scene constants live in a __constant__ table and are read as c[bank][offset] operands of the
+    // FP64 instructions instead of being materialised with two 32-bit moves each.
+    bool constants_in_bank = true;
 };
 
 struct CodegenInfo {

@@ -173,7 +173,7 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
 
     Leaves u = x/w, v = y/h.  Every new value combines one or two earlier values taken from a sliding
     window (so the DAG is deep, and the number of simultaneously live values stays near `window`):
-        sin(k1*p + k2*q + c)    exp(-(p*p))    ln(1 + p*p)    p*q    (p+q)/2
+        sin(k*p + c)   sin(k1*p + k2*q + c)   exp(-(p*p))   ln(1 + p*p)   p*q   (p+q)/2
     all of which map [-1,1] into [-1,1], so nothing overflows.  Values nobody consumed are summed
     into the three channels; channel = 127.5 + 127.5 * clamp(sum/len, -1, 1) via min/max.
     """
@@ -203,14 +203,16 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
     while count < n_values:
         kind = rng.below(100)
         i = pick(); p = pool[i]; uses[i] += 1
-        if kind < 30:
+        if kind < 32:
+            nv = E.sin(E.add(E.mul(rat(1, 9, 2), p), rat(0, 628, 100))); count += 3
+        elif kind < 58:
+            nv = E.exp(E.neg(E.mul(p, p))); count += 3
+        elif kind < 84:
+            nv = E.ln(E.add(E.nat(1), E.mul(p, p))); count += 3
+        elif kind < 92:
             j = pick(); q = pool[j]; uses[j] += 1
             nv = E.sin(E.add(E.add(E.mul(rat(1, 9, 2), p), E.mul(rat(1, 9, 2), q)), rat(0, 628, 100))); count += 5
-        elif kind < 52:
-            nv = E.exp(E.neg(E.mul(p, p))); count += 3
-        elif kind < 74:
-            nv = E.ln(E.add(E.nat(1), E.mul(p, p))); count += 3
-        elif kind < 87:
+        elif kind < 96:
             j = pick(); q = pool[j]; uses[j] += 1
             nv = E.mul(p, q); count += 1
         else:
