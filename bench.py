@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--backend", default="nvrtc", choices=["nvrtc", "interp"])
     ap.add_argument("--cpu-sample-s", type=float, default=12.0, help="target seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--size", default=None, help="WxH override of the workload's frame size (experiments only)")
     return ap.parse_args()
 
 
@@ -208,6 +209,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     scene_bytes, textures, (w, h) = scenes.by_name(args.workload)
+    if args.size:
+        w, h = (int(v) for v in args.size.lower().split("x"))
     r = CudaRenderer(device_ids=[local_rank])
     r.set_textures(textures)
     r.load(scene_bytes)

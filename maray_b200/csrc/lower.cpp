@@ -1,5 +1,7 @@
 // Expr tree -> hash-consed SSA program.  See program.hpp for the contract.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 
@@ -281,14 +283,132 @@ void lower_job(void* arg) {
     for (int c = 0; c < 3; c++) P->root[c] = remap[roots[c]];
     P->n_textures = uint32_t(j->tex->size());
     P->order.clear();
+    // Two candidate schedules: (a) the depth-first order above, (b) the order in which the scene
+    // itself introduces values (Let definitions in file order, then the bodies).  Depth-first keeps
+    // tree-shaped scenes short-lived; authored order wins on wide DAGs whose roots gather values
+    // from everywhere.  Keep whichever needs fewer simultaneously live values.
+    std::vector<uint32_t> dfs_order, authored;
+    for (size_t i = 0; i < P->nodes.size(); i++)
+        if (P->nodes[i].op != OP_CONST) dfs_order.push_back(uint32_t(i));
+    for (size_t i = 0; i < all.size(); i++)
+        if (remap[i] != NONE && all[i].op != OP_CONST) authored.push_back(remap[i]);
+    auto max_live = [&](const std::vector<uint32_t>& ord) {
+        std::vector<uint32_t> uses(P->nodes.size(), 0);
+        for (uint32_t id : ord) {
+            const Node& n = P->nodes[id];
+            if (op_is_unary(n.op) || op_is_binary(n.op)) uses[n.a]++;
+            if (op_is_binary(n.op)) uses[n.b]++;
+        }
+        for (int c = 0; c < 3; c++) uses[P->root[c]]++;
+        uint32_t live = 0, peak = 0;
+        for (uint32_t id : ord) {
+            const Node& n = P->nodes[id];
+            live++;
+            peak = std::max(peak, live);
+            auto done = [&](uint32_t v) {
+                if (P->nodes[v].op == OP_CONST) return;
+                if (--uses[v] == 0) live--;
+            };
+            if (op_is_unary(n.op) || op_is_binary(n.op)) done(n.a);
+            if (op_is_binary(n.op)) done(n.b);
+        }
+        return peak;
+    };
+    // (c) greedy list scheduling: among the values whose operands are ready, take the one that
+    // shrinks the live set most (frees the most operands), preferring the most recently enabled one
+    // so that chains stay chains.  Myopic, but it handles DAGs where both fixed orders blow up.
+    // position of every value in the authored order (tie-break for the "oldest first" variant)
+    std::vector<uint32_t> authored_pos(P->nodes.size(), 0);
+    for (size_t i = 0; i < authored.size(); i++) authored_pos[authored[i]] = uint32_t(i);
+    auto greedy_schedule = [&](bool oldest_first) {
+        std::vector<uint32_t> greedy;
+        const size_t n = P->nodes.size();
+        std::vector<uint32_t> uses(n, 0), pending(n, 0), stamp(n, 0);
+        std::vector<std::vector<uint32_t>> users(n);
+        auto is_k = [&](uint32_t v) { return P->nodes[v].op == OP_CONST; };
+        for (uint32_t id : dfs_order) {
+            const Node& nd = P->nodes[id];
+            auto dep = [&](uint32_t v) {
+                if (is_k(v)) return;
+                uses[v]++;
+                users[v].push_back(id);
+                pending[id]++;
+            };
+            if (op_is_unary(nd.op) || op_is_binary(nd.op)) dep(nd.a);
+            if (op_is_binary(nd.op) && nd.b != nd.a) dep(nd.b);
+            else if (op_is_binary(nd.op) && !is_k(nd.b)) uses[nd.b]++;   // a == b: one edge, two reads
+        }
+        for (int c = 0; c < 3; c++) uses[P->root[c]]++;
+        auto score = [&](uint32_t id) {
+            const Node& nd = P->nodes[id];
+            int freed = 0;
+            if (op_is_unary(nd.op) || op_is_binary(nd.op)) {
+                uint32_t reads_a = 1 + ((op_is_binary(nd.op) && nd.b == nd.a) ? 1 : 0);
+                if (!is_k(nd.a) && uses[nd.a] == reads_a) freed++;
+                if (op_is_binary(nd.op) && nd.b != nd.a && !is_k(nd.b) && uses[nd.b] == 1) freed++;
+            }
+            return freed;
+        };
+        struct Item { int score; uint32_t stamp; uint32_t id; };
+        auto worse = [](const Item& x, const Item& y) { return x.score != y.score ? x.score < y.score : x.stamp < y.stamp; };
+        std::vector<Item> heap;
+        uint32_t clock = 0;
+        auto push = [&](uint32_t id) {
+            // newest first: chains stay chains (depth-first flavour); oldest first: follow the order
+            // in which the scene introduced the values (breadth never runs far ahead)
+            stamp[id] = oldest_first ? (0xffffffffu - authored_pos[id]) : ++clock;
+            heap.push_back(Item{score(id), stamp[id], id});
+            std::push_heap(heap.begin(), heap.end(), worse);
+        };
+        std::vector<uint8_t> done(n, 0);
+        for (uint32_t id : dfs_order) if (pending[id] == 0) push(id);
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end(), worse);
+            Item it = heap.back();
+            heap.pop_back();
+            if (done[it.id] || it.stamp != stamp[it.id]) continue;   // superseded entry
+            int sc = score(it.id);
+            if (sc != it.score) { heap.push_back(Item{sc, it.stamp, it.id}); std::push_heap(heap.begin(), heap.end(), worse); continue; }
+            done[it.id] = 1;
+            greedy.push_back(it.id);
+            const Node& nd = P->nodes[it.id];
+            auto read = [&](uint32_t v) { if (!is_k(v)) uses[v]--; };
+            if (op_is_unary(nd.op) || op_is_binary(nd.op)) read(nd.a);
+            if (op_is_binary(nd.op)) read(nd.b);
+            for (uint32_t u : users[it.id]) if (--pending[u] == 0) push(u);
+            // users of my operands may now free them: refresh the ready ones lazily (their score is
+            // recomputed when popped; bump the stamp of ready co-users so they are reconsidered early)
+            auto refresh = [&](uint32_t v) {
+                if (is_k(v) || uses[v] != 1) return;
+                for (uint32_t u : users[v]) if (!done[u] && pending[u] == 0) push(u);
+            };
+            if (op_is_unary(nd.op) || op_is_binary(nd.op)) refresh(nd.a);
+            if (op_is_binary(nd.op)) refresh(nd.b);
+        }
+        if (greedy.size() != dfs_order.size()) greedy.clear();   // cannot happen for a DAG; be safe
+        return greedy;
+    };
+    std::vector<uint32_t> greedy_new = greedy_schedule(false), greedy_old = greedy_schedule(true);
+    const std::vector<uint32_t>* cand[4] = {&dfs_order, &authored, &greedy_new, &greedy_old};
+    uint32_t live[4];
+    int best = 0;
+    for (int i = 0; i < 4; i++) {
+        live[i] = cand[i]->size() == dfs_order.size() ? max_live(*cand[i]) : 0xffffffffu;
+        if (live[i] < live[best]) best = i;
+    }
+    const std::vector<uint32_t>& chosen = *cand[best];
     ProgramStats st;
+    st.max_live = live[best];
+    st.schedule_kind = uint32_t(best);
+    if (std::getenv("MARAY_VERBOSE"))
+        std::fprintf(stderr, "maray: max live values  depth-first %u  authored %u  greedy(newest) %u  greedy(oldest) %u\n",
+                     live[0], live[1], live[2], live[3]);
     st.tree_nodes = j->scene->tree_nodes[0] + j->scene->tree_nodes[1] + j->scene->tree_nodes[2];
     st.dag_nodes = P->nodes.size();
     std::vector<uint32_t> depth(P->nodes.size(), 0);
     for (size_t i = 0; i < P->nodes.size(); i++) {
         const Node& n = P->nodes[i];
         if (n.op == OP_CONST) { st.n_const++; continue; }
-        P->order.push_back(uint32_t(i));
         st.op_count[n.op]++;
         switch (n.dep) {
         case DEP_X: st.n_x++; break;
@@ -301,6 +421,7 @@ void lower_job(void* arg) {
         depth[i] = d + 1;
         st.depth = std::max(st.depth, depth[i]);
     }
+    P->order = chosen;
     P->stats = st;
     j->ok = true;
 }

@@ -46,6 +46,8 @@ struct ProgramStats {
     uint64_t n_const = 0, n_x = 0, n_y = 0, n_xy = 0;
     uint64_t op_count[OP_COUNT] = {0};   // per op, non-constant values only
     uint32_t depth = 0;             // longest operand chain
+    uint32_t max_live = 0;          // most values simultaneously live under the chosen schedule
+    uint32_t schedule_kind = 0;     // 0 depth-first, 1 the scene's own order, 2/3 greedy list schedule (newest/oldest first)
 };
 
 struct Program {

@@ -36,11 +36,14 @@ _range = _b.range   # this module defines its own `range`, `min`, `max`, `abs` (
 class Expr:
     """One node.  `a`/`b` are operands, `n` is the Var id / Nat value / App id, `vars` the Let context."""
 
-    __slots__ = ("tag", "a", "b", "n", "vars", "__weakref__")
+    __slots__ = ("tag", "a", "b", "n", "vars", "seq", "__weakref__")
+    _count = 0
 
     def __init__(self, tag: int, a: Optional["Expr"] = None, b: Optional["Expr"] = None, n: int = 0,
                  vars: Optional[Tuple[Tuple[int, "Expr"], ...]] = None):
         self.tag, self.a, self.b, self.n, self.vars = tag, a, b, n, vars
+        Expr._count += 1
+        self.seq = Expr._count          # creation order: operands always have a smaller seq
 
     # operator sugar, as the reference's impl Add/Sub/Mul/Div/Neg (src/lib.rs:151-194)
     def __add__(self, o): return add(self, _lift(o))
@@ -325,17 +328,18 @@ def tree_size(e: Expr) -> int:
     return size[id(e)]
 
 
-def share_let(color: Sequence[Expr], min_tree_size: int = 3) -> List[Expr]:
+def share_let(color: Sequence[Expr], min_tree_size: int = 3, bind: Sequence[Expr] = ()) -> List[Expr]:
     """Express DAG sharing on the wire: one `Let` with ids 0..n (definitions in dependency order,
     definition i may use $j for j<i) placed on top of every channel, bodies rewritten to `Var`s.
 
     This is the canonical shape `Expr::compress` produces (reference src/compressor.rs:215-236) and
     the shape for which var_fixer is the identity: all three channels carry the SAME
     context.  The choice of which sub-terms become variables is ours (every node used more than once
-    whose tree has at least `min_tree_size` nodes); values are unchanged by construction.
-    Channels must be Let-free.
+    whose tree has at least `min_tree_size` nodes, plus every node listed in `bind` -- an author may
+    name any intermediate result); values are unchanged by construction.  Channels must be Let-free.
     """
-    order = dag_nodes(color)
+    # definitions follow the order in which the scene's author built the values (operands first)
+    order = sorted(dag_nodes(color), key=lambda n: n.seq)
     refs: Dict[int, int] = {}
     for n in order:
         assert n.tag != LET, "share_let expects Let-free channels"
@@ -343,6 +347,7 @@ def share_let(color: Sequence[Expr], min_tree_size: int = 3) -> List[Expr]:
             refs[id(c)] = refs.get(id(c), 0) + 1
     for r in color:
         refs[id(r)] = refs.get(id(r), 0) + 1
+    forced = {id(n) for n in bind}
     tsize: Dict[int, int] = {}
     new: Dict[int, Expr] = {}          # node -> rewritten node (shared nodes replaced by Var)
     defs: List[Tuple[int, Expr]] = []
@@ -354,7 +359,8 @@ def share_let(color: Sequence[Expr], min_tree_size: int = 3) -> List[Expr]:
         else:
             rew = _mk(n.tag, new[id(n.a)] if n.a is not None else None,
                       new[id(n.b)] if n.b is not None else None, n.n)
-        if refs.get(id(n), 0) > 1 and tsize[id(n)] >= min_tree_size and n.tag not in (X, Y, TAU, E, NAT, VAR):
+        shared = refs.get(id(n), 0) > 1 and tsize[id(n)] >= min_tree_size
+        if (shared or id(n) in forced) and n.tag not in (X, Y, TAU, E, NAT, VAR):
             vid = len(defs)
             defs.append((vid, rew))
             rew = var_id(vid)

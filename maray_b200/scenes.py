@@ -174,8 +174,8 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
     Leaves u = x/w, v = y/h.  Every new value combines one or two earlier values taken from a sliding
     window (so the DAG is deep, and the number of simultaneously live values stays near `window`):
         sin(k*p + c)   sin(k1*p + k2*q + c)   exp(-(p*p))   ln(1 + p*p)   p*q   (p+q)/2
-    all of which map [-1,1] into [-1,1], so nothing overflows.  Values nobody consumed are summed
-    into the three channels; channel = 127.5 + 127.5 * clamp(sum/len, -1, 1) via min/max.
+    all of which map [-1,1] into [-1,1], so nothing overflows.  Values nobody consumed by the time they
+    leave the window are added to one of three running channel sums; channel = 127.5 + 127.5 * clamp(sum/len, -1, 1) via min/max.
     """
     rng = Lcg(seed)
     u, v = E.div(E.x(), E.nat(w)), E.div(E.y(), E.nat(h))
@@ -200,6 +200,18 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
                 return i
         return lo + rng.below(len(pool) - lo)
 
+    sums: List = [None, None, None]      # running per-channel sums of the values nobody consumed
+    n_summed = [0, 0, 0]
+    retired = 0                          # pool[:retired] has left the window
+
+    named: List[E.Expr] = []             # the running sums are bound to Let variables where they arise
+
+    def fold(val: E.Expr) -> None:
+        c = sum(n_summed) % 3
+        sums[c] = val if sums[c] is None else E.add(sums[c], val)
+        n_summed[c] += 1
+        named.append(sums[c])
+
     while count < n_values:
         kind = rng.below(100)
         i = pick(); p = pool[i]; uses[i] += 1
@@ -219,19 +231,22 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
             j = pick(); q = pool[j]; uses[j] += 1
             nv = E.mul(E.add(p, q), E.half()); count += 2
         pool.append(nv); uses.append(0)
-
-    loose = [pool[i] for i in range(len(pool)) if uses[i] == 0]
+        # values that leave the window unconsumed join a channel sum right away (keeps few values live)
+        while retired < len(pool) - window:
+            if uses[retired] == 0:
+                fold(pool[retired]); count += 1
+            retired += 1
+    for i in range(retired, len(pool)):
+        if uses[i] == 0:
+            fold(pool[i])
     chans = []
     for c in range(3):
-        mine = loose[c::3] or [pool[-1 - c]]
-        acc = mine[0]
-        for it in mine[1:]:
-            acc = E.add(acc, it)
-        mean = E.div(acc, E.nat(len(mine)))
+        acc = sums[c] if sums[c] is not None else pool[-1 - c]
+        mean = E.div(acc, E.nat(max(1, n_summed[c])))
         cl = E.max(E.neg(E.nat(1)), E.min(E.nat(1), mean))
         half255 = E.div(E.nat(255), E.nat(2))
         chans.append(E.add(half255, E.mul(half255, cl)))
-    return E.to_bytes([w, h], E.share_let(chans))
+    return E.to_bytes([w, h], E.share_let(chans, bind=named))
 
 
 def by_name(name: str) -> Tuple[bytes, List[np.ndarray], Tuple[int, int]]:

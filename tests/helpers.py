@@ -29,7 +29,8 @@ HOST_SHIM = r"""
 #define __noinline__
 #define __restrict__
 #define __shared__ static
-#define __launch_bounds__(x)
+#define __constant__ static
+#define __launch_bounds__(...)
 struct uint3_ { unsigned int x, y, z; };
 static uint3_ threadIdx, blockIdx, blockDim;
 struct uint4 { unsigned int x, y, z, w; };
