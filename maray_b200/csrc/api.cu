@@ -210,6 +210,14 @@ int nvrtc_compile(maray_cuda* h) {
 // Interpreter launch shape: as many resident warps as the slot file allows.
 void choose_interp_shape(maray_cuda* h) {
     const size_t budget = 200 * 1024;   // leave room under the 227 KiB per-block limit
+    if (const char* e = std::getenv("MARAY_INTERP_SHAPE")) {   // "block,pixels_per_thread" (tuning)
+        unsigned b = 0, p = 0;
+        if (std::sscanf(e, "%u,%u", &b, &p) == 2 && b % 32 == 0 && (p == 1 || p == 2 || p == 4) &&
+            interp_smem_bytes(b, p, h->bc.n_slots) <= 227 * 1024) {
+            h->interp_block = b; h->interp_ppt = p;
+            return;
+        }
+    }
     const unsigned shapes[][2] = {{256, 2}, {128, 2}, {128, 1}, {64, 1}, {32, 1}};
     for (auto& sh : shapes) {
         if (interp_smem_bytes(sh[0], sh[1], h->bc.n_slots) <= budget) {

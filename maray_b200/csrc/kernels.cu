@@ -83,8 +83,10 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
         }
         const uint64_t* cs = code_s + (c & 1) * kChunk;
         const unsigned int cnt = (n_instr - c * kChunk < (unsigned)kChunk) ? (n_instr - c * kChunk) : (unsigned)kChunk;
+        uint64_t w_next = cs[0];
         for (unsigned int i = 0; i < cnt; i++) {
-            const uint64_t w = cs[i];                     // warp-uniform: broadcast LDS.64
+            const uint64_t w = w_next;                    // warp-uniform: broadcast LDS.64,
+            w_next = cs[i + 1 < cnt ? i + 1 : i];         // fetched one instruction ahead of its use
             const unsigned int lo = (unsigned int)w, operand = (unsigned int)(w >> 32);
             const unsigned int op = lo & 0xffu;
             const double* sp = slots + (size_t)(operand & 0xffffu) * P * B + tid;   // *_S and TEX forms
