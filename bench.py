@@ -141,7 +141,16 @@ class ClockSampler:
         self.reasons = set()
         self.max_mhz = None
         self._stop = threading.Event()
+        self.ready = threading.Event()
         self._th = None
+        self._bits = {}
+        self.t0 = self.t1 = None        # the timed region (perf_counter), set by mark()
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def _run(self):
         try:
@@ -162,30 +171,47 @@ class ClockSampler:
                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
             }
+            self.ready.set()
             while not self._stop.is_set():
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(hnd, nv.NVML_CLOCK_SM)))
+                now = time.perf_counter()
+                mhz = float(nv.nvmlDeviceGetClockInfo(hnd, nv.NVML_CLOCK_SM))
+                mask = 0
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
-                    for name, bit in bits.items():
-                        if mask & bit:
-                            self.reasons.add(name)
                 except Exception:
                     pass
-                self._stop.wait(0.01)
+                self.samples.append((now, mhz, mask))
+                self._bits = bits
+                self._stop.wait(0.002)
         except Exception as exc:   # NVML unavailable: say so instead of inventing numbers
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+            self.ready.set()
 
     def start(self):
+        """Starts sampling (call before the warm-up so NVML is initialised when the timed region begins)."""
         self._th = threading.Thread(target=self._run, daemon=True)
         self._th.start()
+        self.ready.wait(timeout=10)
 
     def stop(self):
         self._stop.set()
         if self._th:
             self._th.join(timeout=6)
-        s = sorted(self.samples)
-        med = s[len(s) // 2] if s else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        inside = [s for s in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= s[0] <= self.t1]
+        scope = "timed region"
+        if not inside and self.samples and self.t0 is not None:
+            # region shorter than the sampling period: take the samples that bracket it
+            before = [s for s in self.samples if s[0] < self.t0][-1:]
+            after = [s for s in self.samples if s[0] > (self.t1 or self.t0)][:1]
+            inside = before + after
+            scope = "samples bracketing the timed region"
+        for _, _, mask in inside:
+            for name, bit in self._bits.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        mhz = sorted(s[1] for s in inside)
+        med = mhz[len(mhz) // 2] if mhz else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(mhz), "scope": scope}
 
 
 # ---- GPU arm --------------------------------------------------------------------------------------
@@ -240,16 +266,17 @@ def run_ours(args):
     # FP64 issue-rate peak of this GPU (roofline denominator), measured before the timed region.
     peak_nofma, peak_fma = r.fp64_peak(0)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_device()
         flush.zero_()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    sampler.mark_start()
     for i in range(args.steps):
         ev[i][0].record(stream)
         kev[i][0].record(stream)
@@ -262,6 +289,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()       # every step starts together on all ranks
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
