@@ -177,6 +177,8 @@ int nvrtc_compile(maray_cuda* h) {
     };
     std::string maxreg = "--maxrregcount=" + std::to_string(h->jit_maxreg);
     if (h->jit_maxreg) opts.push_back(maxreg.c_str());
+    if (const char* e = std::getenv("MARAY_LIBM"))      // A/B: MARAY_LIBM=cuda uses libdevice's sin/exp/log
+        if (std::string(e) == "cuda") opts.push_back("-DMR_LIBM_PLAIN=1");
     nvrtcResult rc = nvrtcCompileProgram(prog, int(opts.size()), opts.data());
     size_t log_size = 0;
     nvrtcGetProgramLogSize(prog, &log_size);

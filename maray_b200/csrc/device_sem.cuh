@@ -8,6 +8,8 @@
 #ifndef MARAY_DEVICE_SEM_CUH
 #define MARAY_DEVICE_SEM_CUH
 
+#include "device_libm.cuh"   // mr_sin / mr_exp / mr_log  (the build inlines this text for NVRTC)
+
 // Step(a): `if v >= 0.0 {1.0} else {0.0}`  (NaN -> 0, -0.0 -> 1).  reference src/lib.rs:644-647
 __device__ __forceinline__ double mr_step(double v) { return (v >= 0.0) ? 1.0 : 0.0; }
 

@@ -120,15 +120,15 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
                 break;
             case BC_SIN:
 #pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = sin(acc[k]);
+                for (int k = 0; k < P; k++) acc[k] = mr_sin(acc[k]);
                 break;
             case BC_EXP:
 #pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = exp(acc[k]);
+                for (int k = 0; k < P; k++) acc[k] = mr_exp(acc[k]);
                 break;
             case BC_LN:
 #pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = log(acc[k]);
+                for (int k = 0; k < P; k++) acc[k] = mr_log(acc[k]);
                 break;
             case BC_ADD_S:
 #pragma unroll

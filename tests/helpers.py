@@ -31,6 +31,8 @@ HOST_SHIM = r"""
 #define __shared__ static
 #define __constant__ static
 #define __launch_bounds__(...)
+#define MR_LIBM_PLAIN 1          /* the host check uses the host libm, like the oracle */
+#define MR_PLAIN_FN static inline
 struct uint3_ { unsigned int x, y, z; };
 static uint3_ threadIdx, blockIdx, blockDim;
 struct uint4 { unsigned int x, y, z, w; };
