@@ -54,6 +54,28 @@ struct Emitter {
         s += buf;
     }
 
+    // Emits order[i..j) -- one batch of same-kind transcendentals -- as x4 / x2 / single out-of-line
+    // calls.  The four (two) bodies inside a call are independent, which is where the FP64 pipe gets
+    // its instruction-level parallelism in transcendental-heavy programs.
+    void batch_calls(std::string& s, const std::vector<uint32_t>& order, size_t i, size_t j) const {
+        const char* fn = P.nodes[order[i]].op == OP_SIN ? "sin" : (P.nodes[order[i]].op == OP_EXP ? "exp" : "log");
+        char buf[96];
+        while (i < j) {
+            size_t k = (j - i >= 4) ? 4 : ((j - i >= 2) ? 2 : 1);
+            if (k == 1) { statement(s, order[i]); i++; continue; }
+            std::snprintf(buf, sizeof buf, "  const MrD%zu b%u = mr_%s_x%zu(", k, order[i], fn, k);
+            s += buf;
+            for (size_t m = 0; m < k; m++) { if (m) s += ", "; operand(s, P.nodes[order[i + m]].a); }
+            s += ");\n";
+            static const char* fld[4] = {"a", "b", "c", "d"};
+            for (size_t m = 0; m < k; m++) {
+                std::snprintf(buf, sizeof buf, "  const double v%u = b%u.%s;\n", order[i + m], order[i], fld[m]);
+                s += buf;
+            }
+            i += k;
+        }
+    }
+
     void statement(std::string& s, uint32_t id) const {
         const Node& n = P.nodes[id];
         if (n.op == OP_X || n.op == OP_Y) return;   // kernel arguments
@@ -135,8 +157,16 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
         src += "__device__ __noinline__ double mr_sin_call(double v) { return mr_sin(v); }\n";
         src += "__device__ __noinline__ double mr_exp_call(double v) { return mr_exp(v); }\n";
         src += "__device__ __noinline__ double mr_log_call(double v) { return mr_log(v); }\n";
+        src += "struct MrD2 { double a, b; };\nstruct MrD4 { double a, b, c, d; };\n";
+        for (const char* fn : {"sin", "exp", "log"}) {
+            std::string f(fn);
+            src += "__device__ __noinline__ MrD2 mr_" + f + "_x2(double a, double b) { MrD2 r; r.a = mr_" + f + "(a); r.b = mr_" + f + "(b); return r; }\n";
+            src += "__device__ __noinline__ MrD4 mr_" + f + "_x4(double a, double b, double c, double d) { MrD4 r; r.a = mr_" + f +
+                   "(a); r.b = mr_" + f + "(b); r.c = mr_" + f + "(c); r.d = mr_" + f + "(d); return r; }\n";
+        }
     }
 
+    const bool use_batches = !em.inline_trans && prog.batch.size() == order.size();
     char buf[256];
     uint32_t frame_slots = 0;
     std::vector<int32_t> slot(prog.nodes.size(), -1);
@@ -209,14 +239,20 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
                 std::snprintf(buf, sizeof buf, "  const double v%u = F[%d];\n", id, slot[id]);
                 src += buf;
             }
-            for (size_t i = lo; i < hi; i++) {
-                uint32_t id = order[i];
-                em.statement(src, id);
-                if (opt.sync_every && (i - lo) % opt.sync_every == opt.sync_every - 1) src += "  __syncthreads();\n";
-                if (slot[id] >= 0) {
-                    std::snprintf(buf, sizeof buf, "  F[%d] = v%u;\n", slot[id], id);
-                    src += buf;
+            for (size_t i = lo; i < hi;) {
+                size_t j = i + 1;
+                if (use_batches && prog.batch[i]) while (j < hi && prog.batch[j] == prog.batch[i]) j++;
+                if (j - i > 1) em.batch_calls(src, order, i, j);
+                else em.statement(src, order[i]);
+                for (size_t m = i; m < j; m++) {
+                    uint32_t id = order[m];
+                    if (opt.sync_every && (m - lo) % opt.sync_every == opt.sync_every - 1) src += "  __syncthreads();\n";
+                    if (slot[id] >= 0) {
+                        std::snprintf(buf, sizeof buf, "  F[%d] = v%u;\n", slot[id], id);
+                        src += buf;
+                    }
                 }
+                i = j;
             }
             src += "}\n";
         }
@@ -247,9 +283,14 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
         }
     } else {
         uint32_t since_sync = 0;
-        for (uint32_t id : order) {
-            em.statement(src, id);
-            if (opt.sync_every && ++since_sync >= opt.sync_every) { src += "  __syncthreads();\n"; since_sync = 0; }
+        for (size_t i = 0; i < order.size();) {
+            size_t j = i + 1;
+            if (use_batches && prog.batch[i]) while (j < order.size() && prog.batch[j] == prog.batch[i]) j++;
+            if (j - i > 1) em.batch_calls(src, order, i, j);
+            else em.statement(src, order[i]);
+            since_sync += uint32_t(j - i);
+            if (opt.sync_every && since_sync >= opt.sync_every) { src += "  __syncthreads();\n"; since_sync = 0; }
+            i = j;
         }
     }
     src += "  mr_store_block(p, stage, ";

@@ -16,7 +16,7 @@ struct CodegenOptions {
     uint32_t segment_values = 16384;
     // sin/exp/ln are inlined below this many transcendental values, called out-of-line above it
     // (their inlined bodies dominate code size and compile time in transcendental-heavy scenes).
-    uint32_t inline_transcendentals_below = 2048;
+    uint32_t inline_transcendentals_below = kOutOfLineTranscendentals;
     // Threads per block of the generated kernel (a multiple of 32; one pixel per thread).
     uint32_t block = 256;
     // __launch_bounds__ second argument: resident blocks per SM the register allocation must allow

@@ -421,7 +421,77 @@ void lower_job(void* arg) {
         depth[i] = d + 1;
         st.depth = std::max(st.depth, depth[i]);
     }
-    P->order = chosen;
+    // Transcendental batching: pull later sin/exp/ln values of the same kind (and the few cheap values
+    // they need) forward so that up to kBatchMax independent ones sit next to each other.  Bounded
+    // look-ahead, so live ranges barely change; evaluation order never changes values.
+    uint64_t n_trans_total = 0;
+    for (const Node& nd : P->nodes) n_trans_total += (nd.op == OP_SIN || nd.op == OP_EXP || nd.op == OP_LN);
+    if (n_trans_total < kOutOfLineTranscendentals) {
+        P->order = chosen;
+        P->batch.assign(chosen.size(), 0);
+    } else {
+        constexpr uint32_t kBatchMax = 8, kWindow = 384, kConeMax = 24;
+        const size_t n = P->nodes.size();
+        std::vector<uint32_t> pos(n, NONE);
+        for (size_t i = 0; i < chosen.size(); i++) pos[chosen[i]] = uint32_t(i);
+        std::vector<uint8_t> emitted(n, 0);
+        for (size_t i = 0; i < n; i++) if (P->nodes[i].op == OP_CONST) emitted[i] = 1;
+        std::vector<uint32_t> out, out_batch;
+        out.reserve(chosen.size());
+        out_batch.reserve(chosen.size());
+        auto is_trans = [&](uint32_t v) { Op o = P->nodes[v].op; return o == OP_SIN || o == OP_EXP || o == OP_LN; };
+        uint32_t next_batch = 0;
+        std::vector<uint32_t> cone, stack_;
+        std::vector<uint8_t> in_batch(n, 0);
+        for (size_t p0 = 0; p0 < chosen.size(); p0++) {
+            uint32_t id = chosen[p0];
+            if (emitted[id]) continue;
+            if (!is_trans(id)) { emitted[id] = 1; out.push_back(id); out_batch.push_back(0); continue; }
+            std::vector<uint32_t> members{id};
+            in_batch[id] = 1;
+            uint32_t scanned = 0;
+            for (size_t j = p0 + 1; j < chosen.size() && scanned < kWindow && members.size() < kBatchMax; j++) {
+                uint32_t c = chosen[j];
+                if (emitted[c]) continue;
+                scanned++;
+                if (P->nodes[c].op != P->nodes[id].op) continue;
+                // the not-yet-evaluated values c needs: small, free of transcendentals, independent of the batch
+                cone.clear();
+                stack_.clear();
+                bool ok = true;
+                auto visit = [&](uint32_t v) {
+                    if (emitted[v]) return;
+                    if (in_batch[v] || is_trans(v)) { ok = false; return; }
+                    if (std::find(cone.begin(), cone.end(), v) != cone.end()) return;
+                    cone.push_back(v);
+                    stack_.push_back(v);
+                };
+                visit(P->nodes[c].a);
+                while (ok && !stack_.empty() && cone.size() <= kConeMax) {
+                    uint32_t v = stack_.back();
+                    stack_.pop_back();
+                    const Node& nv = P->nodes[v];
+                    if (op_is_unary(nv.op) || op_is_binary(nv.op)) visit(nv.a);
+                    if (ok && op_is_binary(nv.op)) visit(nv.b);
+                }
+                if (!ok || cone.size() > kConeMax) continue;
+                std::sort(cone.begin(), cone.end(), [&](uint32_t x, uint32_t y) { return pos[x] < pos[y]; });
+                for (uint32_t v : cone) { emitted[v] = 1; out.push_back(v); out_batch.push_back(0); }
+                members.push_back(c);
+                in_batch[c] = 1;
+            }
+            uint32_t tag = members.size() > 1 ? ++next_batch : 0;
+            for (uint32_t v : members) {
+                emitted[v] = 1;
+                in_batch[v] = 0;
+                out.push_back(v);
+                out_batch.push_back(tag);
+            }
+            if (tag) { st.n_batches++; st.n_batched += uint32_t(members.size()); }
+        }
+        P->order.swap(out);
+        P->batch.swap(out_batch);
+    }
     P->stats = st;
     j->ok = true;
 }

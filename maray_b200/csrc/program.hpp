@@ -40,6 +40,10 @@ struct Node {
 
 struct TextureDim { uint32_t w, h; };
 
+// Programs with at least this many sin/exp/ln values evaluate them out of line (the NVRTC back end
+// calls batched helper functions instead of inlining every body) and get their schedule batched.
+constexpr uint32_t kOutOfLineTranscendentals = 2048;
+
 struct ProgramStats {
     uint64_t tree_nodes = 0;        // nodes of the three channel trees as stored
     uint64_t dag_nodes = 0;         // values after hash-consing, reachable from the channel roots
@@ -47,6 +51,7 @@ struct ProgramStats {
     uint64_t op_count[OP_COUNT] = {0};   // per op, non-constant values only
     uint32_t depth = 0;             // longest operand chain
     uint32_t max_live = 0;          // most values simultaneously live under the chosen schedule
+    uint32_t n_batches = 0, n_batched = 0;   // transcendental batches formed / values in them
     uint32_t schedule_kind = 0;     // 0 depth-first, 1 the scene's own order, 2/3 greedy list schedule (newest/oldest first)
 };
 
@@ -54,6 +59,10 @@ struct Program {
     std::vector<Node> nodes;        // topological: operands precede users; every node is reachable
     uint32_t root[3] = {0, 0, 0};   // R, G, B
     std::vector<uint32_t> order;    // evaluation order of the non-constant values (a schedule)
+    // batch[i] for order[i]: 0 = not batched; otherwise consecutive entries with the same non-zero id
+    // are sin/exp/ln values of one kind that are mutually independent and whose operands all precede
+    // the first of them -- they may be evaluated together (instruction-level parallelism, one call).
+    std::vector<uint32_t> batch;
     uint32_t n_textures = 0;        // textures the program was lowered against
     ProgramStats stats;
 };

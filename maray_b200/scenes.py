@@ -260,5 +260,6 @@ def by_name(name: str) -> Tuple[bytes, List[np.ndarray], Tuple[int, int]]:
     if name == "textured":
         return textured(), synthetic_textures(), (3840, 2160)
     if name == "deep":
-        return deep(), [], (8192, 8192)
+        # MARAY_DEEP_VALUES shrinks the program for quick experiments (the benchmark config is 100 000)
+        return deep(n_values=int(os.environ.get("MARAY_DEEP_VALUES", "100000"))), [], (8192, 8192)
     raise KeyError(name)
