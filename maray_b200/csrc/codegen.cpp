@@ -157,13 +157,6 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
         src += "__device__ __noinline__ double mr_sin_call(double v) { return mr_sin(v); }\n";
         src += "__device__ __noinline__ double mr_exp_call(double v) { return mr_exp(v); }\n";
         src += "__device__ __noinline__ double mr_log_call(double v) { return mr_log(v); }\n";
-        src += "struct MrD2 { double a, b; };\nstruct MrD4 { double a, b, c, d; };\n";
-        for (const char* fn : {"sin", "exp", "log"}) {
-            std::string f(fn);
-            src += "__device__ __noinline__ MrD2 mr_" + f + "_x2(double a, double b) { MrD2 r; r.a = mr_" + f + "(a); r.b = mr_" + f + "(b); return r; }\n";
-            src += "__device__ __noinline__ MrD4 mr_" + f + "_x4(double a, double b, double c, double d) { MrD4 r; r.a = mr_" + f +
-                   "(a); r.b = mr_" + f + "(b); r.c = mr_" + f + "(c); r.d = mr_" + f + "(d); return r; }\n";
-        }
     }
 
     const bool use_batches = !em.inline_trans && prog.batch.size() == order.size();

@@ -22,6 +22,16 @@
 MR_PLAIN_FN double mr_sin(double x) { return sin(x); }
 MR_PLAIN_FN double mr_exp(double x) { return exp(x); }
 MR_PLAIN_FN double mr_log(double x) { return log(x); }
+struct MrD2 { double a, b; };
+struct MrD4 { double a, b, c, d; };
+#define MR_DEFINE_BATCHED(fn)                                                                                   \
+    MR_PLAIN_FN MrD2 mr_##fn##_x2(double a, double b) { MrD2 r; r.a = mr_##fn(a); r.b = mr_##fn(b); return r; }  \
+    MR_PLAIN_FN MrD4 mr_##fn##_x4(double a, double b, double c, double d) {                                     \
+        MrD4 r; r.a = mr_##fn(a); r.b = mr_##fn(b); r.c = mr_##fn(c); r.d = mr_##fn(d); return r;               \
+    }
+MR_DEFINE_BATCHED(sin)
+MR_DEFINE_BATCHED(exp)
+MR_DEFINE_BATCHED(log)
 #else
 
 #ifdef MR_LIBM_HOST
@@ -102,8 +112,14 @@ static __device__ __align__(16) const double MR_SINCOS[2][6] = {
 // sin(x).  Fast range |x| < 2^22: Cody-Waite reduction by pi/2 with three FMAs, quadrant from the
 // low bits of the magic sum, one 7-step Horner chain whose coefficients depend on the quadrant's
 // parity.  Everything else (incl. NaN, infinity) goes to libdevice.
-MR_FN double mr_sin(double x) {
-    if (!(fabs(x) < 4194304.0)) return MR_SLOW_SIN(x);
+// The range tests look at the high word only (integer pipe, not the FP64 pipe); NaN and infinity
+// have a high word above every bound, so they always take the libdevice branch.
+MR_FN int mr_sin_inrange(double x) { return (unsigned int)(mr_hi32(x) & 0x7fffffff) < 0x41500000u; }   // |x| < 2^22
+MR_FN int mr_exp_inrange(double x) { return (unsigned int)(mr_hi32(x) & 0x7fffffff) < 0x40862000u; }   // |x| < 708
+MR_FN int mr_log_inrange(double x) { return (unsigned int)(mr_hi32(x) - 0x00100000) < 0x7fe00000u; }   // positive normal
+
+// Straight-line fast paths: safe (no traps, no loops) for ANY argument, meaningful inside the range.
+MR_FN double mr_sin_fast(double x) {
     const double t = MR_FMA(x, MR_LK[1], MR_LK[0]);
     const double q = t - MR_LK[0];
     double r = MR_FMA(q, -MR_LK[2], x);
@@ -129,11 +145,15 @@ MR_FN double mr_sin(double x) {
     const double v = odd ? p : sn;
     return mr_hilo((int)((unsigned int)mr_hi32(v) ^ (((unsigned int)qi & 2u) << 30)), mr_lo32(v));   // quadrants 2,3: negate
 }
+MR_FN double mr_sin(double x) {
+    double r = mr_sin_fast(x);
+    if (!mr_sin_inrange(x)) r = MR_SLOW_SIN(x);
+    return r;
+}
 
 // exp(x).  Fast range |x| < 708: n = rint(x*log2(e)), r = x - n*ln2 (two FMAs), degree-12 polynomial,
 // scaling by 2^n through the exponent field.
-MR_FN double mr_exp(double x) {
-    if (!(fabs(x) < 708.0)) return MR_SLOW_EXP(x);
+MR_FN double mr_exp_fast(double x) {
     const double t = MR_FMA(x, MR_LK[5], MR_LK[0]);
     const double n = t - MR_LK[0];
     double r = MR_FMA(n, -MR_LK[6], x);
@@ -153,14 +173,18 @@ MR_FN double mr_exp(double x) {
     p = MR_FMA(p, r, 1.0);
     return mr_hilo((int)((unsigned int)mr_hi32(p) + ((unsigned int)mr_lo32(t) << 20)), mr_lo32(p));
 }
+MR_FN double mr_exp(double x) {
+    double r = mr_exp_fast(x);
+    if (!mr_exp_inrange(x)) r = MR_SLOW_EXP(x);
+    return r;
+}
 
 // log(x).  Fast range: positive normal finite x.  x = m * 2^e with m in [sqrt(1/2), sqrt(2));
 // u = 2(m-1)/(m+1) from an approximate reciprocal refined by two Newton steps, with the exact
 // remainder of that division carried as u_lo; log(m) = u + u_lo + u^3*Q(u^2); the sum with e*ln2
 // is compensated.
-MR_FN double mr_log(double x) {
+MR_FN double mr_log_fast(double x) {
     const int hx = mr_hi32(x);
-    if (!((unsigned int)(hx - 0x00100000) < 0x7fe00000u)) return MR_SLOW_LOG(x);
     int e = (hx >> 20) - 1023;
     int mh = (hx & 0x000fffff) | 0x3ff00000;
     if (mh >= 0x3ff6a09f) { mh -= 0x00100000; e += 1; }
@@ -192,6 +216,43 @@ MR_FN double mr_log(double x) {
     const double lo = MR_FMA(ed, MR_LK[7], t3) + c;
     return h + lo;
 }
+MR_FN double mr_log(double x) {
+    double r = mr_log_fast(x);
+    if (!mr_log_inrange(x)) r = MR_SLOW_LOG(x);
+    return r;
+}
+
+#ifndef MR_LIBM_HOST
+// Batched forms for the out-of-line path of the NVRTC back end: the straight-line fast paths of all
+// arguments first (independent dependency chains for the FP64 pipe), then ONE rarely taken branch
+// that repairs whichever arguments were out of range.
+struct MrD2 { double a, b; };
+struct MrD4 { double a, b, c, d; };
+#define MR_DEFINE_BATCHED(fn)                                                                          \
+    static __device__ __noinline__ MrD2 mr_##fn##_x2(double a, double b) {                             \
+        MrD2 r;                                                                                        \
+        r.a = mr_##fn##_fast(a); r.b = mr_##fn##_fast(b);                                              \
+        if (!(mr_##fn##_inrange(a) & mr_##fn##_inrange(b))) {                                          \
+            if (!mr_##fn##_inrange(a)) r.a = mr_slow_##fn(a);                                          \
+            if (!mr_##fn##_inrange(b)) r.b = mr_slow_##fn(b);                                          \
+        }                                                                                              \
+        return r;                                                                                      \
+    }                                                                                                  \
+    static __device__ __noinline__ MrD4 mr_##fn##_x4(double a, double b, double c, double d) {         \
+        MrD4 r;                                                                                        \
+        r.a = mr_##fn##_fast(a); r.b = mr_##fn##_fast(b); r.c = mr_##fn##_fast(c); r.d = mr_##fn##_fast(d); \
+        if (!(mr_##fn##_inrange(a) & mr_##fn##_inrange(b) & mr_##fn##_inrange(c) & mr_##fn##_inrange(d))) { \
+            if (!mr_##fn##_inrange(a)) r.a = mr_slow_##fn(a);                                          \
+            if (!mr_##fn##_inrange(b)) r.b = mr_slow_##fn(b);                                          \
+            if (!mr_##fn##_inrange(c)) r.c = mr_slow_##fn(c);                                          \
+            if (!mr_##fn##_inrange(d)) r.d = mr_slow_##fn(d);                                          \
+        }                                                                                              \
+        return r;                                                                                      \
+    }
+MR_DEFINE_BATCHED(sin)
+MR_DEFINE_BATCHED(exp)
+MR_DEFINE_BATCHED(log)
+#endif
 
 #endif  // MR_LIBM_PLAIN
 #endif  // MARAY_DEVICE_LIBM_CUH
