@@ -153,12 +153,6 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
         }
         src += "};\n#define MRK(i) (reinterpret_cast<const double*>(MRK_BITS)[i])\n";
     }
-    if (!em.inline_trans) {
-        src += "__device__ __noinline__ double mr_sin_call(double v) { return mr_sin(v); }\n";
-        src += "__device__ __noinline__ double mr_exp_call(double v) { return mr_exp(v); }\n";
-        src += "__device__ __noinline__ double mr_log_call(double v) { return mr_log(v); }\n";
-    }
-
     const bool use_batches = !em.inline_trans && prog.batch.size() == order.size();
     char buf[256];
     uint32_t frame_slots = 0;
