@@ -34,6 +34,25 @@ METRIC = "render_throughput"
 UNIT = "Mpixel/s"
 
 
+def committed_dram_traffic(workload: str, backend: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary of this
+    workload (profiles/rNN_<workload>_<backend>_ncu_full_summary.txt), or None when there is none."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{workload.replace('_', '')}_{backend}_ncu_full_summary.txt"))):
+        total, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        found = 0
+        for line in open(path):
+            m = re.match(r"dram__bytes_(read|write)\.sum \[(\w+)\] = ([0-9.eE+-]+)", line)
+            if m:
+                total += float(m.group(3)) * unit_scale.get(m.group(2), 1.0)
+                found += 1
+        if found == 2:
+            best = {"bytes": total, "source": os.path.relpath(path, ROOT)}
+    return best
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,6 +352,7 @@ def run_ours(args):
         band_px = (y1 - y0) * w
         achieved = band_px * ops_px / (kernel_ms_max * 1e-3) / 1e12
         peak = peak_nofma / 1e12
+        traffic = committed_dram_traffic(args.workload, args.backend) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -346,7 +366,9 @@ def run_ours(args):
             "gpu_launches": args.steps * world,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "Tlaneop/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None,
+                         "traffic": traffic["bytes"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None,
                          "peak_source": "measured live: maray_cuda_fp64_peak DADD/DMUL issue rate (no FMA)",
                          "peak_dfma": peak_fma / 1e12, "kernel_ms": kernel_ms_max,
                          "hbm_bytes_per_launch_algorithmic": band_px * 3},

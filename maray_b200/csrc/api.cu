@@ -51,6 +51,9 @@ struct Gpu {
     // back ends
     cudaLibrary_t lib = nullptr;
     cudaKernel_t jit_kernel = nullptr;
+    cudaKernel_t jit_pre_x = nullptr, jit_pre_y = nullptr;
+    double* d_colv = nullptr; size_t colv_cap = 0;     // hoisting tables (doubles)
+    double* d_rowv = nullptr; size_t rowv_cap = 0;
     uint64_t* d_code = nullptr;
     double* d_consts = nullptr;
     double* d_sink = nullptr;
@@ -75,6 +78,7 @@ struct maray_cuda {
     unsigned interp_block = 128, interp_ppt = 2;
     unsigned jit_block = 256;
     unsigned jit_maxreg = 0;
+    unsigned jit_ncol = 0, jit_nrow = 0;               // hoisted values per column / per row
     maray_cuda_stats stats{};
     int report_kind = MARAY_REPORT_NONE;
     uint32_t report_every = 0;
@@ -100,7 +104,9 @@ int fail(maray_cuda* h, int code, const std::string& msg) {
 void release_backend(maray_cuda* h) {
     for (Gpu& g : h->gpus) {
         cudaSetDevice(g.device);
-        if (g.lib) { cudaLibraryUnload(g.lib); g.lib = nullptr; g.jit_kernel = nullptr; }
+        if (g.lib) { cudaLibraryUnload(g.lib); g.lib = nullptr; g.jit_kernel = nullptr; g.jit_pre_x = g.jit_pre_y = nullptr; }
+        if (g.d_colv) { cudaFree(g.d_colv); g.d_colv = nullptr; g.colv_cap = 0; }
+        if (g.d_rowv) { cudaFree(g.d_rowv); g.d_rowv = nullptr; g.rowv_cap = 0; }
         if (g.d_code) { cudaFree(g.d_code); g.d_code = nullptr; }
         if (g.d_consts) { cudaFree(g.d_consts); g.d_consts = nullptr; }
     }
@@ -236,8 +242,39 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
     p.out = d_out; p.f64_out = d_f64; p.f64_plane = f64_plane; p.tex = g.d_textab;
     p.p0 = p0; p.n = n; p.W = w;
     p.out_aligned = (reinterpret_cast<uintptr_t>(d_out) % 16 == 0) ? 1u : 0u;
+    p.colv = nullptr; p.rowv = nullptr; p.row_base = 0; p.rows = 0;
     if (n == 0) return MARAY_OK;
     if (h->backend == MARAY_BACKEND_NVRTC) {
+        if (h->jit_ncol || h->jit_nrow) {
+            // Prologue: x-only values once per column, y-only values once per row of this launch.
+            const uint32_t y_first = p0 / w, y_last = (p0 + n - 1) / w, rows = y_last - y_first + 1;
+            const size_t need_c = std::max<size_t>(size_t(h->jit_ncol) * w, 1), need_r = std::max<size_t>(size_t(h->jit_nrow) * rows, 1);
+            if (g.colv_cap < need_c) {
+                if (g.d_colv) cudaFree(g.d_colv);
+                g.d_colv = nullptr; g.colv_cap = 0;
+                CU_TRY(h, cudaMalloc(&g.d_colv, need_c * sizeof(double)));
+                g.colv_cap = need_c;
+            }
+            if (g.rowv_cap < need_r) {
+                if (g.d_rowv) cudaFree(g.d_rowv);
+                g.d_rowv = nullptr; g.rowv_cap = 0;
+                CU_TRY(h, cudaMalloc(&g.d_rowv, need_r * sizeof(double)));
+                g.rowv_cap = need_r;
+            }
+            const MrTexture* tex = g.d_textab;
+            uint32_t base = 0;
+            if (h->jit_ncol) {
+                uint32_t cnt = w;
+                void* a[] = {&g.d_colv, &cnt, &base, &tex};
+                CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_pre_x), dim3((cnt + 127) / 128), dim3(128), a, 0, stream));
+            }
+            if (h->jit_nrow) {
+                uint32_t cnt = rows, ybase = y_first;
+                void* a[] = {&g.d_rowv, &cnt, &ybase, &tex};
+                CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_pre_y), dim3((cnt + 127) / 128), dim3(128), a, 0, stream));
+            }
+            p.colv = g.d_colv; p.rowv = g.d_rowv; p.row_base = y_first; p.rows = rows;
+        }
         void* args[] = {&p};
         unsigned grid = (n + h->jit_block - 1) / h->jit_block;
         CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, 0, stream));
@@ -477,6 +514,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         if (const char* e = std::getenv("MARAY_JIT_INLINE_TRANS_BELOW")) copt.inline_transcendentals_below = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_SYNC_EVERY")) copt.sync_every = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_CONST_BANK")) copt.constants_in_bank = std::strtoul(e, nullptr, 10) != 0;
+        if (const char* e = std::getenv("MARAY_JIT_HOIST")) copt.hoist = std::strtoul(e, nullptr, 10) != 0;
         if (const char* e = std::getenv("MARAY_JIT_BLOCK")) copt.block = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10));
         h->jit_maxreg = 0;
@@ -484,6 +522,8 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         h->source = generate_cuda_source(h->prog, copt, &info);
         h->stats.codegen_ms = now_ms() - t1;
         h->jit_block = info.block;
+        h->jit_ncol = info.n_col;
+        h->jit_nrow = info.n_row;
         h->stats.jit_segments = info.segments;
         h->stats.jit_frame_slots = info.frame_slots;
         h->stats.jit_source_bytes = uint32_t(h->source.size());
@@ -517,6 +557,10 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
             if (backend == MARAY_BACKEND_NVRTC) {
                 CU_TRY(h, cudaLibraryLoadData(&g.lib, h->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
                 CU_TRY(h, cudaLibraryGetKernel(&g.jit_kernel, g.lib, kJitKernelName));
+                if (h->jit_ncol || h->jit_nrow) {
+                    CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_x, g.lib, kJitPreXName));
+                    CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_y, g.lib, kJitPreYName));
+                }
             } else {
                 CU_TRY(h, cudaMalloc(&g.d_code, h->bc.code.size() * sizeof(uint64_t)));
                 CU_TRY(h, cudaMemcpy(g.d_code, h->bc.code.data(), h->bc.code.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));

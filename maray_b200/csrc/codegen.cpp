@@ -36,6 +36,9 @@ struct Emitter {
     const Program& P;
     bool inline_trans;
     const std::vector<int32_t>* bank_index;   // value id -> index in the __constant__ table, or -1
+    // In the per-pixel kernel a hoisted value is a load from its table: 1 = column table, 2 = row table.
+    const std::vector<uint8_t>* load_kind = nullptr;
+    const std::vector<uint32_t>* table_index = nullptr;
 
     void operand(std::string& s, uint32_t id) const {
         const Node& n = P.nodes[id];
@@ -80,6 +83,12 @@ struct Emitter {
         const Node& n = P.nodes[id];
         if (n.op == OP_X || n.op == OP_Y) return;   // kernel arguments
         char buf[160];
+        if (load_kind && (*load_kind)[id]) {
+            if ((*load_kind)[id] == 1) std::snprintf(buf, sizeof buf, "  const double v%u = __ldg(CV + %uu * CW);\n", id, (*table_index)[id]);
+            else std::snprintf(buf, sizeof buf, "  const double v%u = __ldg(RV + %uu * RW);\n", id, (*table_index)[id]);
+            s += buf;
+            return;
+        }
         std::snprintf(buf, sizeof buf, "  const double v%u = ", id);
         s += buf;
         auto un = [&](const char* pre, const char* post) { s += pre; operand(s, n.a); s += post; };
@@ -114,7 +123,38 @@ struct Emitter {
 }  // namespace
 
 std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt, CodegenInfo* info) {
-    const std::vector<uint32_t>& order = prog.order;
+    // The per-pixel kernel evaluates the values that depend on both x and y; x-only / y-only frontier
+    // values are loaded from the column / row tables (each at its first use), the x-only / y-only
+    // values behind them are evaluated by the two prologue kernels only.
+    const bool hoist = opt.hoist && (!prog.col_values.empty() || !prog.row_values.empty());
+    std::vector<uint8_t> load_kind(prog.nodes.size(), 0);
+    std::vector<uint32_t> table_index(prog.nodes.size(), 0);
+    std::vector<uint32_t> order, order_batch;
+    if (hoist) {
+        for (size_t k = 0; k < prog.col_values.size(); k++) { load_kind[prog.col_values[k]] = 1; table_index[prog.col_values[k]] = uint32_t(k); }
+        for (size_t k = 0; k < prog.row_values.size(); k++) { load_kind[prog.row_values[k]] = 2; table_index[prog.row_values[k]] = uint32_t(k); }
+        std::vector<uint8_t> loaded(prog.nodes.size(), 0);
+        for (size_t i = 0; i < prog.order.size(); i++) {
+            uint32_t id = prog.order[i];
+            const Node& n = prog.nodes[id];
+            if (n.op == OP_X || n.op == OP_Y) continue;
+            if (n.dep == DEP_X || n.dep == DEP_Y) continue;          // prologue work
+            auto need = [&](uint32_t v) {
+                if (load_kind[v] && !loaded[v]) { loaded[v] = 1; order.push_back(v); order_batch.push_back(0); }
+            };
+            if (op_is_unary(n.op) || op_is_binary(n.op)) need(n.a);
+            if (op_is_binary(n.op)) need(n.b);
+            order.push_back(id);
+            order_batch.push_back(prog.batch.size() == prog.order.size() ? prog.batch[i] : 0);
+        }
+        for (int c = 0; c < 3; c++) {
+            uint32_t r = prog.root[c];
+            if (load_kind[r] && !loaded[r]) { loaded[r] = 1; order.push_back(r); order_batch.push_back(0); }
+        }
+    } else {
+        order = prog.order;
+        order_batch = prog.batch.size() == prog.order.size() ? prog.batch : std::vector<uint32_t>(prog.order.size(), 0);
+    }
     uint64_t n_trans = prog.stats.op_count[OP_SIN] + prog.stats.op_count[OP_EXP] + prog.stats.op_count[OP_LN];
     // __constant__ table of the scene's constants (64 KiB bank: at most 8000 entries; the rest
     // stay literals).  Stored as bit patterns so NaN/infinity need no special spelling.
@@ -134,6 +174,8 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
         }
     }
     Emitter em{prog, n_trans < opt.inline_transcendentals_below, opt.constants_in_bank ? &bank_index : nullptr};
+    Emitter em_pre = em;                       // prologue kernels compute hoisted values, never load them
+    if (hoist) { em.load_kind = &load_kind; em.table_index = &table_index; }
 
     const uint32_t seg_len = opt.segment_values ? opt.segment_values : 4096;
     const bool segmented = order.size() > seg_len;
@@ -153,7 +195,7 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
         }
         src += "};\n#define MRK(i) (reinterpret_cast<const double*>(MRK_BITS)[i])\n";
     }
-    const bool use_batches = !em.inline_trans && prog.batch.size() == order.size();
+    const bool use_batches = !em.inline_trans;
     char buf[256];
     uint32_t frame_slots = 0;
     std::vector<int32_t> slot(prog.nodes.size(), -1);
@@ -202,7 +244,8 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
             size_t lo = size_t(s) * seg_len, hi = std::min(order.size(), lo + seg_len);
             std::snprintf(buf, sizeof buf,
                           "__device__ __noinline__ void mr_seg%u(double* __restrict__ F, const double X, const double Y, "
-                          "const MrTexture* __restrict__ T) {\n", s);
+                          "const MrTexture* __restrict__ T, const double* __restrict__ CV, const unsigned int CW, "
+                          "const double* __restrict__ RV, const unsigned int RW) {\n", s);
             src += buf;
             // imports: values defined in earlier segments and read here
             std::vector<uint32_t> imports;
@@ -228,7 +271,7 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
             }
             for (size_t i = lo; i < hi;) {
                 size_t j = i + 1;
-                if (use_batches && prog.batch[i]) while (j < hi && prog.batch[j] == prog.batch[i]) j++;
+                if (use_batches && order_batch[i]) while (j < hi && order_batch[j] == order_batch[i]) j++;
                 if (j - i > 1) em.batch_calls(src, order, i, j);
                 else em.statement(src, order[i]);
                 for (size_t m = i; m < j; m++) {
@@ -261,18 +304,21 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
     src += "  const unsigned int xi = pix - yi * p.W;\n";
     src += "  const double X = (double)xi;\n  const double Y = (double)yi;\n";   // `x as f64`
     src += "  const MrTexture* __restrict__ T = p.tex;\n  (void)T;\n";
+    src += "  const double* __restrict__ CV = p.colv + xi;\n  const unsigned int CW = p.W;\n";
+    src += "  const double* __restrict__ RV = p.rowv + (yi - p.row_base);\n  const unsigned int RW = p.rows;\n";
+    src += "  (void)CV; (void)CW; (void)RV; (void)RW;\n";
     if (segmented) {
         std::snprintf(buf, sizeof buf, "  double F[%u];\n", frame_slots ? frame_slots : 1);
         src += buf;
         for (uint32_t s = 0; s < n_seg; s++) {
-            std::snprintf(buf, sizeof buf, "  mr_seg%u(F, X, Y, T);\n", s);
+            std::snprintf(buf, sizeof buf, "  mr_seg%u(F, X, Y, T, CV, CW, RV, RW);\n", s);
             src += buf;
         }
     } else {
         uint32_t since_sync = 0;
         for (size_t i = 0; i < order.size();) {
             size_t j = i + 1;
-            if (use_batches && prog.batch[i]) while (j < order.size() && prog.batch[j] == prog.batch[i]) j++;
+            if (use_batches && order_batch[i]) while (j < order.size() && order_batch[j] == order_batch[i]) j++;
             if (j - i > 1) em.batch_calls(src, order, i, j);
             else em.statement(src, order[i]);
             since_sync += uint32_t(j - i);
@@ -293,11 +339,36 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
     }
     src += "active, j);\n}\n";
 
+    // Prologue kernels: one thread per column / per row evaluates the x-only / y-only sub-program and
+    // stores its frontier values (k-major, so the per-pixel kernel's column loads are coalesced and
+    // its row loads are a broadcast).
+    if (hoist) {
+        for (int which = 1; which <= 2; which++) {
+            const bool colk = which == 1;
+            src += colk ? "extern \"C\" __global__ void maray_pre_x(double* __restrict__ tab, const unsigned int n, const unsigned int base, const MrTexture* __restrict__ T) {\n"
+                        : "extern \"C\" __global__ void maray_pre_y(double* __restrict__ tab, const unsigned int n, const unsigned int base, const MrTexture* __restrict__ T) {\n";
+            src += "  const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;\n  if (t >= n) return;\n  (void)T;\n";
+            src += colk ? "  const double X = (double)(base + t);\n" : "  const double Y = (double)(base + t);\n";
+            for (uint32_t id : prog.order) {
+                const Node& n = prog.nodes[id];
+                if (n.op == OP_X || n.op == OP_Y || n.dep != (colk ? DEP_X : DEP_Y)) continue;
+                em_pre.statement(src, id);
+                if (load_kind[id] == which) {
+                    std::snprintf(buf, sizeof buf, "  tab[%uu * n + t] = v%u;\n", table_index[id], id);
+                    src += buf;
+                }
+            }
+            src += "}\n";
+        }
+    }
+
     if (info) {
         info->segments = n_seg;
         info->frame_slots = segmented ? frame_slots : 0;
         info->transcendentals_inlined = em.inline_trans;
         info->block = block;
+        info->n_col = hoist ? uint32_t(prog.col_values.size()) : 0;
+        info->n_row = hoist ? uint32_t(prog.row_values.size()) : 0;
     }
     return src;
 }

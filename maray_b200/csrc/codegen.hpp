@@ -30,6 +30,9 @@ struct CodegenOptions {
     // Scene constants live in a __constant__ table and are read as c[bank][offset] operands of the
     // FP64 instructions instead of being materialised with two 32-bit moves each.
     bool constants_in_bank = true;
+    // Evaluate x-only / y-only values once per column / row in prologue kernels and load them in the
+    // per-pixel kernel (the GPU form of the reference's row cache).
+    bool hoist = true;
 };
 
 struct CodegenInfo {
@@ -37,10 +40,13 @@ struct CodegenInfo {
     uint32_t frame_slots = 0;       // doubles of per-thread frame (0 when not segmented)
     bool transcendentals_inlined = true;
     uint32_t block = 256;           // threads per block the kernel must be launched with
+    uint32_t n_col = 0, n_row = 0;  // doubles per column / per row in the hoisting tables (0 = no prologue)
 };
 
-// Name of the generated kernel (extern "C").
+// Names of the generated kernels (extern "C").
 extern const char* const kJitKernelName;
+constexpr const char* kJitPreXName = "maray_pre_x";
+constexpr const char* kJitPreYName = "maray_pre_y";
 
 std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt, CodegenInfo* info);
 

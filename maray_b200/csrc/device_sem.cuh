@@ -66,6 +66,11 @@ struct MrParams {
     const MrTexture* tex;      // device texture table (may be null when the program has no App)
     unsigned int p0, n, W;
     unsigned int out_aligned;  // out is 16-byte aligned: full blocks store uint4
+    // Hoisted values (NVRTC back end): colv[k*W + x] = k-th x-only frontier value at column x;
+    // rowv[k*rows + (y - row_base)] = k-th y-only frontier value at row y.
+    const double* colv;
+    const double* rowv;
+    unsigned int row_base, rows;
 };
 
 // Packs one pixel into the block's staging tile and writes the tile with coalesced 16-byte
