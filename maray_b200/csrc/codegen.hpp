@@ -31,8 +31,11 @@ struct CodegenOptions {
     // FP64 instructions instead of being materialised with two 32-bit moves each.
     bool constants_in_bank = true;
     // Evaluate x-only / y-only values once per column / row in prologue kernels and load them in the
-    // per-pixel kernel (the GPU form of the reference's row cache).
-    bool hoist = true;
+    // per-pixel kernel (the GPU form of the reference's row cache).  OFF by default: measured on
+    // B200 it LOSES (chess_4k 9.95 ms vs 7.77 ms, sdf 0.225 vs 0.184 ms) -- the 417 table loads per
+    // pixel cost more issue slots and exposed latency than the 1 227 mostly one-instruction values
+    // they replace.  Kept as MARAY_JIT_HOIST=1 for scenes with expensive x-only/y-only sub-programs.
+    bool hoist = false;
 };
 
 struct CodegenInfo {
