@@ -221,14 +221,14 @@ void choose_interp_shape(maray_cuda* h) {
     if (const char* e = std::getenv("MARAY_INTERP_SHAPE")) {   // "block,pixels_per_thread" (tuning)
         unsigned b = 0, p = 0;
         if (std::sscanf(e, "%u,%u", &b, &p) == 2 && b % 32 == 0 && (p == 1 || p == 2 || p == 4) &&
-            interp_smem_bytes(b, p, h->bc.n_slots) <= 227 * 1024) {
+            interp_smem_bytes(b, p, h->bc.n_slots, unsigned(h->bc.consts.size())) <= 227 * 1024) {
             h->interp_block = b; h->interp_ppt = p;
             return;
         }
     }
     const unsigned shapes[][2] = {{256, 2}, {128, 2}, {128, 1}, {64, 1}, {32, 1}};
     for (auto& sh : shapes) {
-        if (interp_smem_bytes(sh[0], sh[1], h->bc.n_slots) <= budget) {
+        if (interp_smem_bytes(sh[0], sh[1], h->bc.n_slots, unsigned(h->bc.consts.size())) <= budget) {
             h->interp_block = sh[0]; h->interp_ppt = sh[1];
             return;
         }
@@ -279,8 +279,8 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
         unsigned grid = (n + h->jit_block - 1) / h->jit_block;
         CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, 0, stream));
     } else {
-        CU_TRY(h, launch_interp(p, g.d_code, unsigned(h->bc.code.size()), g.d_consts, h->bc.n_slots, h->interp_block,
-                                h->interp_ppt, stream));
+        CU_TRY(h, launch_interp(p, g.d_code, unsigned(h->bc.code.size()), g.d_consts, unsigned(h->bc.consts.size()),
+                                h->bc.n_slots, h->interp_block, h->interp_ppt, stream));
     }
     return MARAY_OK;
 }
@@ -536,7 +536,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         h->stats.jit_cubin_bytes = uint32_t(h->cubin.size());
     } else {
         if (!compile_bytecode(h->prog, &h->bc, &err)) return fail(h, MARAY_E_COMPILE, err);
-        if (h->bc.code.size() & 1) h->bc.code.push_back(bc_encode(BC_END, 0));   // 16-byte cp.async granules
+        if (h->bc.code.size() & 1) h->bc.code.push_back(bc_encode(BC_END, 0, 0, 0, 0));   // 16-byte cp.async granules
         choose_interp_shape(h);
         if (!h->interp_block)
             return fail(h, MARAY_E_UNSUPPORTED, "program needs " + std::to_string(h->bc.n_slots) +

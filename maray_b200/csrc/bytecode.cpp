@@ -1,4 +1,4 @@
-// SSA program -> accumulator bytecode.  See bytecode.hpp for the format.
+// SSA program -> accumulator bytecode (version 2).  See bytecode.hpp for the format.
 //
 // One linear pass over the program's schedule.  The running value stays in the accumulator; a value
 // is written to a slot only if somebody other than the very next instruction needs it.  Slots are
@@ -32,6 +32,7 @@ public:
             if (op_is_unary(nd.op) || op_is_binary(nd.op)) uses_left[nd.a]++;
             if (op_is_binary(nd.op)) uses_left[nd.b]++;
         }
+        if (B.consts.size() > 0xffff) { err = "program has more than 65535 distinct constants"; return; }
         for (int c = 0; c < 3; c++) uses_left[P.root[c]]++;
         // X and Y are preloaded into slots 0 and 1 and stay there.
         for (size_t i = 0; i < n; i++) {
@@ -55,13 +56,12 @@ public:
         // channels whose value is a constant, X or Y (everything else was written when computed)
         static const BcOp outs[3] = {BC_OUT_R, BC_OUT_G, BC_OUT_B};
         for (int c = 0; c < 3 && err.empty(); c++) {
-            Op o = P.nodes[P.root[c]].op;
-            if (o == OP_CONST || o == OP_X || o == OP_Y) {
-                to_acc(P.root[c]);
-                emit(outs[c], 0);
-            }
+            uint32_t r = P.root[c];
+            Op o = P.nodes[r].op;
+            if (o == OP_CONST) emit(outs[c], BC_F_SWAP | BC_F_B_CONST, 0, 0, uint32_t(kidx[r]));
+            else if (o == OP_X || o == OP_Y) emit(outs[c], 0, 0, uint32_t(slot[r]), 0);
         }
-        emit(BC_END, 0);
+        emit(BC_END, 0, 0, 0, 0);
     }
 
 private:
@@ -71,35 +71,31 @@ private:
     std::vector<int32_t> slot, kidx;
     std::vector<uint32_t> free_slots;
     uint32_t acc_holds = NONE;
+    int32_t last_stored = -1;        // slot written by the previous instruction, or -1
 
     bool is_const(uint32_t id) const { return P.nodes[id].op == OP_CONST; }
     bool has_slot(uint32_t id) const { return slot[id] >= 0; }
-    bool avail(uint32_t id) const { return is_const(id) || has_slot(id); }
 
     uint32_t alloc_slot() {
         if (!free_slots.empty()) { uint32_t s = free_slots.back(); free_slots.pop_back(); return s; }
         if (B.n_slots >= 65535) { err = "program needs more than 65535 live values"; return 0; }
         return B.n_slots++;
     }
-    void emit(BcOp op, uint32_t operand) { B.code.push_back(bc_encode(op, operand)); }
+    void emit(BcOp op, uint32_t flags, uint32_t dst, uint32_t a, uint32_t b) {
+        B.code.push_back(bc_encode(op, flags, dst, a, b));
+        last_stored = -1;
+    }
     // The instruction just emitted produced the accumulator value: make it also store to a slot.
     uint32_t store_last() {
         uint32_t s = alloc_slot();
-        B.code.back() |= BC_FLAG_STORE | (uint64_t(s) << 16);
+        B.code.back() |= (uint64_t(BC_F_STORE) << 8) | (uint64_t(s) << 16);
+        last_stored = int32_t(s);
         return s;
     }
     void consume(uint32_t id) {
         if (is_const(id)) return;
         if (uses_left[id] == 0) { err = "internal: value consumed more often than it is used"; return; }
         if (--uses_left[id] == 0 && slot[id] >= 2) { free_slots.push_back(uint32_t(slot[id])); slot[id] = -1; }
-    }
-
-    void to_acc(uint32_t id) {
-        if (acc_holds == id && !is_const(id)) return;
-        if (is_const(id)) { emit(BC_LD_K, uint32_t(kidx[id])); acc_holds = NONE; return; }
-        if (!has_slot(id)) { err = "internal: operand is neither in the accumulator nor in a slot"; return; }
-        emit(BC_LD_S, uint32_t(slot[id]));
-        acc_holds = id;
     }
 
     // Does `user` read `id`, and can it take it from the accumulator?
@@ -111,92 +107,94 @@ private:
         return false;
     }
 
+    // Operand fields for `first` (a value that is in the accumulator or in a slot).
+    bool first_fields(uint32_t v, uint32_t* flags, uint32_t* a) {
+        if (acc_holds == v && !is_const(v)) { *flags |= BC_F_ACC_A; *a = 0; return true; }
+        if (has_slot(v)) { *a = uint32_t(slot[v]); return true; }
+        err = "internal: first operand is neither in the accumulator nor in a slot";
+        return false;
+    }
+    // Operand fields for `second` (slot, constant, or the value the previous instruction stored).
+    bool second_fields(uint32_t v, uint32_t* flags, uint32_t* b) {
+        if (is_const(v)) { *flags |= BC_F_B_CONST; *b = uint32_t(kidx[v]); return true; }
+        if (!has_slot(v)) { err = "internal: second operand is not in a slot"; return false; }
+        *b = uint32_t(slot[v]);
+        if (slot[v] == last_stored) *flags |= BC_F_FWD_B;
+        return true;
+    }
+
     void gen(uint32_t id, uint32_t next) {
         const Node& n = P.nodes[id];
-        int32_t tmp = -1;
+        uint32_t flags = 0, a = 0, b = 0;
         if (op_is_unary(n.op)) {
-            to_acc(n.a);
-            if (!err.empty()) return;
-            emit(BcOp(BC_NEG + (n.op - OP_NEG)), 0);
+            if (!first_fields(n.a, &flags, &a)) return;
+            emit(BcOp(BC_NEG + (n.op - OP_NEG)), flags, 0, a, 0);
             consume(n.a);
         } else {
-            uint32_t a = n.a, b = n.b;
-            const bool tex = n.op == OP_TEX;
-            // the operand that is NOT in the accumulator must be addressable: a slot, or (except for
-            // texture coordinates) a constant
-            auto addressable = [&](uint32_t v) { return tex ? has_slot(v) : avail(v); };
-            bool a_in_acc;
-            if (acc_holds == a && !is_const(a) && addressable(b)) a_in_acc = true;
-            else if (acc_holds == b && !is_const(b) && addressable(a)) a_in_acc = false;
-            else if (is_const(b)) a_in_acc = true;        // load a, then `op constant`
-            else if (is_const(a)) a_in_acc = false;       // load b, then `constant op` (reversed form)
-            else a_in_acc = true;                         // both in slots: load a, then `op slot`
-            uint32_t via_acc = a_in_acc ? a : b, other = a_in_acc ? b : a;
-            if (tex && is_const(other)) {                 // a constant coordinate must sit in a slot
-                emit(BC_LD_K, uint32_t(kidx[other]));
+            // first = the operand taken from the accumulator (if any), else a slot operand;
+            // SWAP when `first` is the node's second argument.
+            uint32_t first = n.a, second = n.b;
+            bool swap = false;
+            if (acc_holds == n.a && !is_const(n.a)) { /* keep */ }
+            else if (acc_holds == n.b && !is_const(n.b)) { first = n.b; second = n.a; swap = true; }
+            else if (is_const(n.a)) { first = n.b; second = n.a; swap = true; }   // a constant can only be `second`
+            uint32_t tmp = NONE;
+            if (is_const(first)) {
+                // both operands constant: only App reaches here (arithmetic was folded).  Put one in a slot.
+                emit(BC_MOV, BC_F_SWAP | BC_F_B_CONST, 0, 0, uint32_t(kidx[first]));
+                tmp = store_last();
                 acc_holds = NONE;
-                tmp = int32_t(store_last());
-            }
-            uint32_t other_operand;
-            bool k = false;
-            if (tmp >= 0) other_operand = uint32_t(tmp);
-            else if (is_const(other)) { k = true; other_operand = uint32_t(kidx[other]); }
-            else if (has_slot(other)) other_operand = uint32_t(slot[other]);
-            else { err = "internal: second operand is not addressable"; return; }
-            to_acc(via_acc);
-            if (!err.empty()) return;
+                a = tmp;
+            } else if (!first_fields(first, &flags, &a)) return;
+            if (swap) flags |= BC_F_SWAP;
+            if (!second_fields(second, &flags, &b)) return;
             BcOp op = BC_END;
+            uint32_t dst = 0;
             switch (n.op) {
-            case OP_ADD: op = k ? BC_ADD_K : BC_ADD_S; break;          // commutative: one form
-            case OP_MUL: op = k ? BC_MUL_K : BC_MUL_S; break;
-            case OP_MAX: op = a_in_acc ? (k ? BC_MAX_K : BC_MAX_S) : (k ? BC_MAXR_K : BC_MAXR_S); break;
-            case OP_MIN: op = a_in_acc ? (k ? BC_MIN_K : BC_MIN_S) : (k ? BC_MINR_K : BC_MINR_S); break;
+            case OP_ADD: op = BC_ADD; break;
+            case OP_MUL: op = BC_MUL; break;
+            case OP_MAX: op = BC_MAX; break;
+            case OP_MIN: op = BC_MIN; break;
             case OP_TEX:
                 if (n.imm > 0xffff) { err = "texture index too large for the interpreter back end"; return; }
-                // TEX: x = slot, y = acc.  TEXR: x = acc, y = slot.
-                op = a_in_acc ? BC_TEXR_S : BC_TEX_S;
-                other_operand |= n.imm << 16;
+                op = BC_TEX; dst = n.imm;
                 break;
             default: err = "internal: unexpected binary op"; return;
             }
-            emit(op, other_operand);
-            consume(a);
-            consume(b);
-            if (tmp >= 0) free_slots.push_back(uint32_t(tmp));
+            emit(op, flags, dst, a, b);
+            if (tmp != NONE) free_slots.push_back(tmp);
+            consume(n.a);
+            consume(n.b);
         }
         if (!err.empty()) return;
         acc_holds = id;
-        // channel outputs are written the moment their value exists
         static const BcOp outs[3] = {BC_OUT_R, BC_OUT_G, BC_OUT_B};
-        // A slot is needed unless the only remaining reader is the next instruction via the accumulator.
         uint32_t root_refs = 0;
         for (int c = 0; c < 3; c++) if (P.root[c] == id) root_refs++;
         uint32_t other_uses = uses_left[id] - root_refs;
+        // A slot is needed unless the only remaining reader is the next instruction via the accumulator.
         if (other_uses > 1 || (other_uses == 1 && !next_takes_from_acc(id, next))) {
+            if (n.op == OP_TEX) emit(BC_MOV, BC_F_ACC_A, 0, 0, 0);   // TEX uses the dst field for its texture id
             slot[id] = int32_t(store_last());
         }
+        // channel outputs are written the moment their value exists
         for (int c = 0; c < 3; c++) {
-            if (P.root[c] == id) { emit(outs[c], 0); consume(id); }
+            if (P.root[c] == id) {
+                emit(outs[c], BC_F_ACC_A, 0, 0, 0);
+                consume(id);
+            }
         }
     }
 };
-
-struct Job { const Program* p; Bytecode* b; std::string err; };
-void job_main(void* arg) {
-    Job* j = static_cast<Job*>(arg);
-    BcGen g(*j->p, *j->b);
-    g.run();
-    j->err = g.err;
-}
 
 }  // namespace
 
 bool compile_bytecode(const Program& prog, Bytecode* out, std::string* err) {
     out->code.clear();
     out->consts.clear();
-    Job j{&prog, out, {}};
-    job_main(&j);
-    if (!j.err.empty()) { if (err) *err = j.err; return false; }
+    BcGen g(prog, *out);
+    g.run();
+    if (!g.err.empty()) { if (err) *err = g.err; return false; }
     if (out->consts.empty()) out->consts.push_back(0.0);
     return true;
 }

@@ -1,17 +1,23 @@
-// Bytecode of the interpreter back end: a flat, static-single-pass register program with one
-// accumulator per pixel and numbered value slots.
+// Bytecode of the interpreter back end: a flat, single-pass register program with one accumulator
+// per pixel and numbered value slots (version 2).
 //
-// Why an accumulator machine: the per-pixel slots live in shared memory, and shared-memory
-// bandwidth (128 B/clk/SM), not the FP64 pipe, bounds a three-address design (24 B of slot traffic
-// per FP64 operation).  Keeping the running value in a register and letting every instruction
-// optionally store its result cuts that to 8-16 B (DESIGN.md "Interpreter kernel").
+// Why this shape: the per-pixel slots live in shared memory, and shared-memory capacity and latency
+// -- not the FP64 pipe -- bound the interpreter.  Every instruction is
+//
+//      acc = op(first, second);   if (ST) slot[dst] = acc
+//
+// where `first` is the accumulator (ACC_A) or slot[a] and `second` is slot[b], constant[b] (B_CONST)
+// or the accumulator (FWD_B: b is the slot the previous instruction just stored).  Keeping chains in
+// the accumulator saves slot traffic; naming both operands lets the kernel fetch the NEXT
+// instruction's operands while the current one executes (the loop is latency-bound otherwise).
 //
 // Instruction word (64 bit):
 //   bits  0.. 7  opcode (BcOp)
-//   bit   8      store flag: after the operation, slot[dst] = acc
-//   bits 16..31  dst slot
-//   bits 32..63  operand: slot index (*_S), constant-pool index (*_K),
-//                or for BC_TEX*: low 16 bits slot index, high 16 bits texture*4 + channel
+//   bits  8..15  flags (BC_F_*)
+//   bits 16..31  dst slot (BC_TEX: texture*4 + channel instead; TEX never stores)
+//   bits 32..47  a: slot index of the first operand (ignored with ACC_A)
+//   bits 48..63  b: slot or constant index of the second operand
+// SWAP evaluates op(second, first) -- f64::max/min and App are not symmetric (NaN / +-0 / x,y).
 // Slot 0 holds X and slot 1 holds Y (`x as f64`, `y as f64`) when the program starts.
 #pragma once
 #include <cstdint>
@@ -24,17 +30,19 @@ namespace maray {
 
 enum BcOp : uint8_t {
     BC_END = 0,
-    BC_LD_S, BC_LD_K,                                   // acc = operand
-    BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,   // acc = f(acc)
-    BC_ADD_S, BC_ADD_K, BC_MUL_S, BC_MUL_K,             // acc = acc op operand
-    BC_MAX_S, BC_MAX_K, BC_MAXR_S, BC_MAXR_K,           // MAX: max(acc, operand); MAXR: max(operand, acc)
-    BC_MIN_S, BC_MIN_K, BC_MINR_S, BC_MINR_K,
-    BC_TEX_S, BC_TEXR_S,                                // TEX: tex(x=operand, y=acc); TEXR: tex(x=acc, y=operand)
-    BC_OUT_R, BC_OUT_G, BC_OUT_B,                       // channel value = acc
+    BC_MOV,                                            // acc = first (or second with SWAP)
+    BC_ADD, BC_MUL, BC_MAX, BC_MIN,                    // acc = first op second
+    BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,   // acc = f(first)
+    BC_TEX,                                            // acc = texture(dst field)(x = first, y = second)
+    BC_OUT_R, BC_OUT_G, BC_OUT_B,                      // channel value = first
     BC_COUNT
 };
 
-constexpr uint32_t BC_FLAG_STORE = 1u << 8;
+constexpr uint32_t BC_F_STORE = 1u;      // slot[dst] = acc after the operation
+constexpr uint32_t BC_F_ACC_A = 2u;      // first operand is the accumulator
+constexpr uint32_t BC_F_SWAP = 4u;       // compute op(second, first)
+constexpr uint32_t BC_F_B_CONST = 8u;    // second operand is constant[b]
+constexpr uint32_t BC_F_FWD_B = 16u;     // second operand is the accumulator (slot b was stored by the previous instruction)
 
 struct Bytecode {
     std::vector<uint64_t> code;      // ends with BC_END
@@ -42,7 +50,10 @@ struct Bytecode {
     uint32_t n_slots = 2;            // including X and Y
 };
 
-inline uint64_t bc_encode(BcOp op, uint32_t operand) { return uint64_t(op) | (uint64_t(operand) << 32); }
+inline uint64_t bc_encode(BcOp op, uint32_t flags, uint32_t dst, uint32_t a, uint32_t b) {
+    return uint64_t(op) | (uint64_t(flags & 0xff) << 8) | (uint64_t(dst & 0xffff) << 16) | (uint64_t(a & 0xffff) << 32) |
+           (uint64_t(b & 0xffff) << 48);
+}
 
 bool compile_bytecode(const Program& prog, Bytecode* out, std::string* err);
 

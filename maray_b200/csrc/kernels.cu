@@ -15,16 +15,20 @@
 namespace maray {
 
 // ------------------------------------------------------------------------------------------------
-// Bytecode interpreter.
+// Bytecode interpreter (bytecode.hpp, version 2).
 //
-// Mapping: one thread evaluates P pixels (P independent dependency chains hide FP64 and shared-
-// memory latency); a block of B threads covers B*P consecutive pixels of the linear image index.
-// Per-pixel value slots live in shared memory as slots[slot][k][tid] (consecutive threads hit
-// consecutive 8-byte words: conflict-free).  The instruction stream is warp-uniform: it is staged
-// from global memory into shared memory in double-buffered chunks with cp.async and every warp
-// reads the same word (a broadcast), so there is no divergence anywhere in the loop.
-// The accumulator-machine encoding (bytecode.hpp) keeps slot traffic to at most one 8-byte load
-// and one optional 8-byte store per FP64 operation.
+// Mapping: one thread evaluates P pixels (P independent dependency chains); a block of B threads
+// covers B*P consecutive pixels of the linear image index.  Per-pixel value slots live in shared
+// memory as slots[slot][k][tid] (consecutive threads hit consecutive 8-byte words: conflict-free),
+// the constant pool is copied to shared memory once per block (read as a broadcast).  The
+// instruction stream is warp-uniform: it is staged from global memory into shared memory in
+// double-buffered chunks with cp.async and every warp reads the same word (a broadcast), so there is
+// no divergence anywhere in the loop.
+//
+// The loop is software-pipelined: while instruction i executes, instruction i+1 is fetched and BOTH
+// of its operands are loaded (speculatively -- flags decide later which of them are used).  The one
+// read-after-write case this cannot see, an operand stored by instruction i itself, is marked by the
+// host compiler (ACC_A / FWD_B: take the accumulator instead).
 
 constexpr int kChunk = 512;   // instructions per staged chunk (4 KiB)
 
@@ -37,17 +41,18 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <int P>
 __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code, unsigned int n_instr,
-                             const double* __restrict__ consts) {
+                             const double* __restrict__ consts, unsigned int n_consts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [2][kChunk] instruction words | staging tile (3*B*P bytes, 16-aligned) | slots
+    // layout: [2][kChunk] instruction words | staging tile (3*B*P bytes, 16-aligned) | constants | slots
     uint64_t* code_s = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned char* stage = smem_raw + 2 * kChunk * sizeof(uint64_t);
     const unsigned int B = blockDim.x;
     const unsigned int tid = threadIdx.x;
-    double* slots = reinterpret_cast<double*>(stage + ((3u * B * P + 15u) & ~15u));
+    double* consts_s = reinterpret_cast<double*>(stage + ((3u * B * P + 15u) & ~15u));
+    double* slots = consts_s + ((n_consts + 1u) & ~1u);
 
     const unsigned int first = blockIdx.x * B * P;
-    double acc[P];
+    double acc[P], va[P], vb[P];
     double out_r[P], out_g[P], out_b[P];
 #pragma unroll
     for (int k = 0; k < P; k++) {
@@ -57,20 +62,31 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
         unsigned int xi = pix - yi * p.W;
         slots[(0 * P + k) * B + tid] = (double)xi;      // `x as f64`, reference src/render.rs:25
         slots[(1 * P + k) * B + tid] = (double)yi;
-        acc[k] = 0.0; out_r[k] = 0.0; out_g[k] = 0.0; out_b[k] = 0.0;
+        acc[k] = 0.0; va[k] = 0.0; vb[k] = 0.0; out_r[k] = 0.0; out_g[k] = 0.0; out_b[k] = 0.0;
     }
+    for (unsigned int i = tid; i < n_consts; i += B) consts_s[i] = consts[i];
 
     const unsigned int n_chunks = (n_instr + kChunk - 1) / kChunk;
-    // prefetch chunk 0
-    for (unsigned int i = tid; i < kChunk / 2; i += B) {
+    for (unsigned int i = tid; i < kChunk / 2; i += B) {   // prefetch chunk 0
         unsigned int idx = i * 2;
         if (idx < n_instr) cp_async16(code_s + idx, code + idx);
     }
     cp_async_commit();
 
+    // operand fetch for one instruction word
+    auto fetch = [&](uint64_t w, double* fa, double* fb) {
+        const unsigned int a = (unsigned int)(w >> 32) & 0xffffu, b = (unsigned int)(w >> 48);
+        const bool bk = (w >> 8) & BC_F_B_CONST;
+        const double* pa = slots + (size_t)a * P * B + tid;
+        const double* pb = bk ? consts_s + b : slots + (size_t)b * P * B + tid;
+        const unsigned int sb = bk ? 0u : B;
+#pragma unroll
+        for (int k = 0; k < P; k++) { fa[k] = pa[k * B]; fb[k] = pb[k * sb]; }
+    };
+
     for (unsigned int c = 0; c < n_chunks; c++) {
         cp_async_wait_all();
-        __syncthreads();   // chunk c landed; every warp is done with chunk c-1
+        __syncthreads();   // chunk c (and, first time, the constants and X/Y slots) landed; chunk c-1 is done
         if (c + 1 < n_chunks) {
             uint64_t* dst = code_s + ((c + 1) & 1) * kChunk;
             const uint64_t* src = code + (size_t)(c + 1) * kChunk;
@@ -83,120 +99,100 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
         }
         const uint64_t* cs = code_s + (c & 1) * kChunk;
         const unsigned int cnt = (n_instr - c * kChunk < (unsigned)kChunk) ? (n_instr - c * kChunk) : (unsigned)kChunk;
-        uint64_t w_next = cs[0];
+        uint64_t w = cs[0];
+        fetch(w, va, vb);                                  // the chunk's first instruction: not overlapped
         for (unsigned int i = 0; i < cnt; i++) {
-            const uint64_t w = w_next;                    // warp-uniform: broadcast LDS.64,
-            w_next = cs[i + 1 < cnt ? i + 1 : i];         // fetched one instruction ahead of its use
-            const unsigned int lo = (unsigned int)w, operand = (unsigned int)(w >> 32);
-            const unsigned int op = lo & 0xffu;
-            const double* sp = slots + (size_t)(operand & 0xffffu) * P * B + tid;   // *_S and TEX forms
-            switch (op) {
-            case BC_LD_S:
+            // ---- stage 1: next instruction's word and operands (overlaps stage 2) -----------------
+            const uint64_t wn = cs[i + 1 < cnt ? i + 1 : i];
+            double na[P], nb[P];
+            fetch(wn, na, nb);
+            // ---- stage 2: execute the current instruction -------------------------------------------
+            const unsigned int lo = (unsigned int)w;
+            const unsigned int op = lo & 0xffu, fl = (lo >> 8) & 0xffu;
+            double x[P], y[P];
 #pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = slots[((size_t)operand * P + k) * B + tid];
-                break;
-            case BC_LD_K: { const double kv = __ldg(consts + operand);
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = kv; } break;
-            case BC_NEG:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = -acc[k];
-                break;
-            case BC_ABS:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = fabs(acc[k]);
-                break;
-            case BC_RECIP:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_recip(acc[k]);
-                break;
-            case BC_SQRT:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_sqrt(acc[k]);
-                break;
-            case BC_STEP:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_step(acc[k]);
-                break;
-            case BC_SIN:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_sin(acc[k]);
-                break;
-            case BC_EXP:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_exp(acc[k]);
-                break;
-            case BC_LN:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_log(acc[k]);
-                break;
-            case BC_ADD_S:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = acc[k] + sp[k * B];
-                break;
-            case BC_ADD_K: { const double kv = __ldg(consts + operand);
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = acc[k] + kv; } break;
-            case BC_MUL_S:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = acc[k] * sp[k * B];
-                break;
-            case BC_MUL_K: { const double kv = __ldg(consts + operand);
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = acc[k] * kv; } break;
-            case BC_MAX_S:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_max(acc[k], sp[k * B]);
-                break;
-            case BC_MAX_K: { const double kv = __ldg(consts + operand);
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_max(acc[k], kv); } break;
-            case BC_MAXR_S:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_max(sp[k * B], acc[k]);
-                break;
-            case BC_MAXR_K: { const double kv = __ldg(consts + operand);
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_max(kv, acc[k]); } break;
-            case BC_MIN_S:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_min(acc[k], sp[k * B]);
-                break;
-            case BC_MIN_K: { const double kv = __ldg(consts + operand);
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_min(acc[k], kv); } break;
-            case BC_MINR_S:
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_min(sp[k * B], acc[k]);
-                break;
-            case BC_MINR_K: { const double kv = __ldg(consts + operand);
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_min(kv, acc[k]); } break;
-            case BC_TEX_S: { const MrTexture t = p.tex[operand >> 18]; const unsigned int ch = (operand >> 16) & 3u;
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_tex(t.data, t.w, t.h, ch, sp[k * B], acc[k]); } break;
-            case BC_TEXR_S: { const MrTexture t = p.tex[operand >> 18]; const unsigned int ch = (operand >> 16) & 3u;
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_tex(t.data, t.w, t.h, ch, acc[k], sp[k * B]); } break;
-            case BC_OUT_R:
-#pragma unroll
-                for (int k = 0; k < P; k++) out_r[k] = acc[k];
-                break;
-            case BC_OUT_G:
-#pragma unroll
-                for (int k = 0; k < P; k++) out_g[k] = acc[k];
-                break;
-            case BC_OUT_B:
-#pragma unroll
-                for (int k = 0; k < P; k++) out_b[k] = acc[k];
-                break;
-            default: break;   // BC_END
+            for (int k = 0; k < P; k++) {
+                const double f = (fl & BC_F_ACC_A) ? acc[k] : va[k];
+                const double s = (fl & BC_F_FWD_B) ? acc[k] : vb[k];
+                x[k] = (fl & BC_F_SWAP) ? s : f;
+                y[k] = (fl & BC_F_SWAP) ? f : s;
             }
-            if (lo & BC_FLAG_STORE) {
+            if (op == BC_MUL) {
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = x[k] * y[k];
+            } else if (op == BC_ADD) {
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = x[k] + y[k];
+            } else if (op == BC_MOV) {
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = x[k];
+            } else if (op == BC_STEP) {
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_step(x[k]);
+            } else if (op == BC_NEG) {
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = -x[k];
+            } else if (op == BC_MIN) {
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_min(x[k], y[k]);
+            } else if (op == BC_MAX) {
+#pragma unroll
+                for (int k = 0; k < P; k++) acc[k] = mr_max(x[k], y[k]);
+            } else {
+                switch (op) {
+                case BC_ABS:
+#pragma unroll
+                    for (int k = 0; k < P; k++) acc[k] = fabs(x[k]);
+                    break;
+                case BC_RECIP:
+#pragma unroll
+                    for (int k = 0; k < P; k++) acc[k] = mr_recip(x[k]);
+                    break;
+                case BC_SQRT:
+#pragma unroll
+                    for (int k = 0; k < P; k++) acc[k] = mr_sqrt(x[k]);
+                    break;
+                case BC_SIN:
+#pragma unroll
+                    for (int k = 0; k < P; k++) acc[k] = mr_sin(x[k]);
+                    break;
+                case BC_EXP:
+#pragma unroll
+                    for (int k = 0; k < P; k++) acc[k] = mr_exp(x[k]);
+                    break;
+                case BC_LN:
+#pragma unroll
+                    for (int k = 0; k < P; k++) acc[k] = mr_log(x[k]);
+                    break;
+                case BC_TEX: {
+                    const unsigned int imm = lo >> 16;
+                    const MrTexture t = p.tex[imm >> 2];
+#pragma unroll
+                    for (int k = 0; k < P; k++) acc[k] = mr_tex(t.data, t.w, t.h, imm & 3u, x[k], y[k]);
+                } break;
+                case BC_OUT_R:
+#pragma unroll
+                    for (int k = 0; k < P; k++) out_r[k] = x[k];
+                    break;
+                case BC_OUT_G:
+#pragma unroll
+                    for (int k = 0; k < P; k++) out_g[k] = x[k];
+                    break;
+                case BC_OUT_B:
+#pragma unroll
+                    for (int k = 0; k < P; k++) out_b[k] = x[k];
+                    break;
+                default: break;   // BC_END
+                }
+            }
+            if (fl & BC_F_STORE) {
                 double* dp = slots + (size_t)(lo >> 16) * P * B + tid;
 #pragma unroll
                 for (int k = 0; k < P; k++) dp[k * B] = acc[k];
             }
+            w = wn;
+#pragma unroll
+            for (int k = 0; k < P; k++) { va[k] = na[k]; vb[k] = nb[k]; }
         }
     }
 
@@ -226,15 +222,17 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
     }
 }
 
-size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_slots) {
+size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_slots, unsigned int n_consts) {
     size_t stage = (3u * (size_t)block * pixels_per_thread + 15u) & ~size_t(15);
-    return 2 * kChunk * sizeof(uint64_t) + stage + (size_t)n_slots * pixels_per_thread * block * sizeof(double);
+    return 2 * kChunk * sizeof(uint64_t) + stage + (size_t)((n_consts + 1u) & ~1u) * sizeof(double) +
+           (size_t)n_slots * pixels_per_thread * block * sizeof(double);
 }
 
 cudaError_t launch_interp(const MrParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
-                          unsigned int n_slots, unsigned int block, unsigned int pixels_per_thread, cudaStream_t stream) {
+                          unsigned int n_consts, unsigned int n_slots, unsigned int block, unsigned int pixels_per_thread,
+                          cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
-    size_t smem = interp_smem_bytes(block, pixels_per_thread, n_slots);
+    size_t smem = interp_smem_bytes(block, pixels_per_thread, n_slots, n_consts);
     unsigned int span = block * pixels_per_thread;
     unsigned int grid = (p.n + span - 1) / span;
     cudaError_t e;
@@ -242,17 +240,17 @@ cudaError_t launch_interp(const MrParams& p, const uint64_t* d_code, unsigned in
     case 1:
         e = cudaFuncSetAttribute(maray_interp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        maray_interp<1><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts);
+        maray_interp<1><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts);
         break;
     case 2:
         e = cudaFuncSetAttribute(maray_interp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        maray_interp<2><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts);
+        maray_interp<2><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts);
         break;
     case 4:
         e = cudaFuncSetAttribute(maray_interp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        maray_interp<4><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts);
+        maray_interp<4><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts);
         break;
     default: return cudaErrorInvalidValue;
     }

@@ -121,32 +121,27 @@ def host_jit_run(source: str, w: int, p0: int, n: int, textures=()):
     return rgb, planes
 
 
-# ---- bytecode ------------------------------------------------------------------------------------
-(BC_END, BC_LD_S, BC_LD_K, BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,
- BC_ADD_S, BC_ADD_K, BC_MUL_S, BC_MUL_K, BC_MAX_S, BC_MAX_K, BC_MAXR_S, BC_MAXR_K,
- BC_MIN_S, BC_MIN_K, BC_MINR_S, BC_MINR_K, BC_TEX_S, BC_TEXR_S, BC_OUT_R, BC_OUT_G, BC_OUT_B) = range(28)
-
-_libm = np.frompyfunc
+# ---- bytecode (csrc/bytecode.hpp, version 2) -------------------------------------------------------
+(BC_END, BC_MOV, BC_ADD, BC_MUL, BC_MAX, BC_MIN, BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,
+ BC_TEX, BC_OUT_R, BC_OUT_G, BC_OUT_B) = range(18)
+F_STORE, F_ACC_A, F_SWAP, F_B_CONST, F_FWD_B = 1, 2, 4, 8, 16
 
 
 def _vec(fn):
-    f = np.frompyfunc(fn, 1, 1)
-
-    def g(a):
-        def safe(v):
-            try:
-                return fn(v)
-            except (ValueError, OverflowError):
-                if fn is math.log:
-                    return -math.inf if v == 0 else math.nan
-                if fn is math.exp:
-                    return math.inf
-                return math.nan
-        return np.frompyfunc(safe, 1, 1)(a).astype(np.float64)
-    return g
+    def safe(v):
+        try:
+            return fn(v)
+        except (ValueError, OverflowError):
+            if fn is math.log:
+                return -math.inf if v == 0 else math.nan
+            if fn is math.exp:
+                return math.inf
+            return math.nan
+    uf = np.frompyfunc(safe, 1, 1)
+    return lambda a: uf(a).astype(np.float64)
 
 
-_sin, _exp, _log = _vec(math.sin), _vec(math.exp), _vec(math.log)
+_sin, _exp, _log = _vec(math.sin), _vec(math.exp), _vec(math.log)      # the host libm, like the oracle
 
 
 def sem_max(a, b):
@@ -178,52 +173,58 @@ def tex_fetch(tex, ch, x, y):
 
 
 def bytecode_run(code, consts, xs, ys, textures=()):
-    """Executes the bytecode for the pixels (xs[i], ys[i]).  Returns planes float64 (3, n)."""
+    """Executes the bytecode for the pixels (xs[i], ys[i]) the way the kernel does, INCLUDING its
+    one-instruction-ahead operand fetch: operands of instruction i+1 are read before instruction i
+    stores, so a program that forgot an ACC_A / FWD_B mark computes a wrong value here too.
+    Returns planes float64 (3, n)."""
     xs = np.asarray(xs, dtype=np.float64)
     ys = np.asarray(ys, dtype=np.float64)
     n = xs.shape[0]
     slots = {0: xs, 1: ys}
+    zero = np.zeros(n)
     acc = np.zeros(n)
     out = np.zeros((3, n))
+
+    def fetch(w):
+        fl, a, b = (w >> 8) & 0xFF, (w >> 32) & 0xFFFF, (w >> 48) & 0xFFFF
+        fa = slots.get(a, zero)
+        fb = np.full(n, consts[b]) if fl & F_B_CONST else slots.get(b, zero)
+        return fa, fb
+
+    words = [int(w) for w in code]
+    va, vb = fetch(words[0])
     with np.errstate(all="ignore"):
-        for w in code:
-            w = int(w)
-            op, store, dst, operand = w & 0xFF, (w >> 8) & 1, (w >> 16) & 0xFFFF, w >> 32
+        for i, w in enumerate(words):
+            nxt = fetch(words[i + 1]) if i + 1 < len(words) else (zero, zero)     # before this instruction's store
+            op, fl, dst = w & 0xFF, (w >> 8) & 0xFF, (w >> 16) & 0xFFFF
             if op == BC_END:
                 break
-            if op == BC_LD_S: acc = slots[operand]
-            elif op == BC_LD_K: acc = np.full(n, consts[operand])
-            elif op == BC_NEG: acc = -acc
-            elif op == BC_ABS: acc = np.abs(acc)
-            elif op == BC_RECIP: acc = 1.0 / acc
-            elif op == BC_SQRT: acc = np.sqrt(acc)
-            elif op == BC_STEP: acc = np.where(acc >= 0.0, 1.0, 0.0)
-            elif op == BC_SIN: acc = _sin(acc)
-            elif op == BC_EXP: acc = _exp(acc)
-            elif op == BC_LN: acc = _log(acc)
-            elif op == BC_ADD_S: acc = acc + slots[operand]
-            elif op == BC_ADD_K: acc = acc + consts[operand]
-            elif op == BC_MUL_S: acc = acc * slots[operand]
-            elif op == BC_MUL_K: acc = acc * consts[operand]
-            elif op == BC_MAX_S: acc = sem_max(acc, slots[operand])
-            elif op == BC_MAX_K: acc = sem_max(acc, np.full(n, consts[operand]))
-            elif op == BC_MAXR_S: acc = sem_max(slots[operand], acc)
-            elif op == BC_MAXR_K: acc = sem_max(np.full(n, consts[operand]), acc)
-            elif op == BC_MIN_S: acc = sem_min(acc, slots[operand])
-            elif op == BC_MIN_K: acc = sem_min(acc, np.full(n, consts[operand]))
-            elif op == BC_MINR_S: acc = sem_min(slots[operand], acc)
-            elif op == BC_MINR_K: acc = sem_min(np.full(n, consts[operand]), acc)
-            elif op == BC_TEX_S:
-                acc = tex_fetch(textures[operand >> 18], (operand >> 16) & 3, slots[operand & 0xFFFF], acc)
-            elif op == BC_TEXR_S:
-                acc = tex_fetch(textures[operand >> 18], (operand >> 16) & 3, acc, slots[operand & 0xFFFF])
-            elif op == BC_OUT_R: out[0] = acc
-            elif op == BC_OUT_G: out[1] = acc
-            elif op == BC_OUT_B: out[2] = acc
+            f = acc if fl & F_ACC_A else va
+            s = acc if fl & F_FWD_B else vb
+            x, y = (s, f) if fl & F_SWAP else (f, s)
+            if op == BC_MOV: acc = x
+            elif op == BC_ADD: acc = x + y
+            elif op == BC_MUL: acc = x * y
+            elif op == BC_MAX: acc = sem_max(x, y)
+            elif op == BC_MIN: acc = sem_min(x, y)
+            elif op == BC_NEG: acc = -x
+            elif op == BC_ABS: acc = np.abs(x)
+            elif op == BC_RECIP: acc = 1.0 / x
+            elif op == BC_SQRT: acc = np.sqrt(x)
+            elif op == BC_STEP: acc = np.where(x >= 0.0, 1.0, 0.0)
+            elif op == BC_SIN: acc = _sin(x)
+            elif op == BC_EXP: acc = _exp(x)
+            elif op == BC_LN: acc = _log(x)
+            elif op == BC_TEX: acc = tex_fetch(textures[dst >> 2], dst & 3, x, y)
+            elif op == BC_OUT_R: out[0] = x
+            elif op == BC_OUT_G: out[1] = x
+            elif op == BC_OUT_B: out[2] = x
             else:
                 raise ValueError(f"bad opcode {op}")
-            if store:
+            if fl & F_STORE:
+                assert op != BC_TEX, "TEX keeps its texture id in the dst field and must not store"
                 slots[dst] = acc
+            va, vb = nxt
     return out
 
 

@@ -102,3 +102,38 @@ def test_nan_inf_and_zero_sign_semantics():
         E.mul(E.step(E.mul(xm, negzero)), E.add(E.mul(inf, xm), E.nat(300))),   # step(-0)=1, inf*0=NaN
     ]
     _check_scene(E.to_bytes([9, 2], color), 9, [0, 1])
+
+
+def test_hoisting_option_is_value_preserving(monkeypatch, chess_bytes):
+    """MARAY_JIT_HOIST=1: x-only / y-only frontier values come from the prologue kernels' tables; every
+    channel value must stay bit-identical (same operations on the same operands, evaluated elsewhere)."""
+    monkeypatch.setenv("MARAY_JIT_HOIST", "1")
+    for scene, w, rows in ((scenes.sdf(320, 200, 16, seed=2), 320, [0, 199]), (chess_bytes, 1024, [512])):
+        with CudaRenderer(gpus=0) as r:
+            r.load(scene)
+            r.compile("nvrtc")
+            src = r.source()
+        assert "maray_pre_x" in src and "maray_pre_y" in src and "__ldg(CV" in src and "__ldg(RV" in src
+        for y in rows:
+            want_rgb, want = _oracle_window(scene, [], 0, w, y, y + 1)
+            rgb, planes = host_jit_run(src, w, y * w, w)
+            assert bits_equal(planes, want.reshape(3, w)).all()
+            assert np.array_equal(rgb, want_rgb.reshape(w, 3))
+
+
+def test_transcendental_batching_keeps_values(monkeypatch):
+    """Programs with >= 2048 sin/exp/ln values get their schedule batched and call x4/x2 helpers."""
+    scene = scenes.deep(48, 32, n_values=9000, seed=3)
+    with CudaRenderer(gpus=0) as r:
+        r.load(scene)
+        st = r.compile("nvrtc")
+        src = r.source()
+        r.compile("interp")
+        code, consts = r.bytecode()
+    assert st["n_sin"] + st["n_exp"] + st["n_ln"] >= 2048
+    assert "_x4(" in src[src.index('extern "C" __global__'):]
+    want_rgb, want = _oracle_window(scene, [], 0, 48, 7, 8)
+    rgb, planes = host_jit_run(src, 48, 7 * 48, 48)
+    assert bits_equal(planes, want.reshape(3, 48)).all() and np.array_equal(rgb, want_rgb.reshape(48, 3))
+    bc = bytecode_run(code, consts, np.arange(48), np.full(48, 7))
+    assert bits_equal(bc, want.reshape(3, 48)).all()
