@@ -226,7 +226,8 @@ void choose_interp_shape(maray_cuda* h) {
             return;
         }
     }
-    const unsigned shapes[][2] = {{256, 2}, {128, 2}, {128, 1}, {64, 1}, {32, 1}};
+    // more resident warps beat more pixels per thread (measured: 256x1 is 15-30 % faster than 128x2)
+    const unsigned shapes[][2] = {{256, 2}, {256, 1}, {128, 1}, {64, 1}, {32, 1}};
     for (auto& sh : shapes) {
         if (interp_smem_bytes(sh[0], sh[1], h->bc.n_slots, unsigned(h->bc.consts.size())) <= budget) {
             h->interp_block = sh[0]; h->interp_ppt = sh[1];
