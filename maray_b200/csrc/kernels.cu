@@ -43,7 +43,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // chess_1k 37.3 vs 40.6 ms, but the transcendental-heavy deep scene 28.9 vs 23.5 ms.)
 template <int P>
 __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code, unsigned int n_instr,
-                             const double* __restrict__ consts, unsigned int n_consts) {
+                             const double* __restrict__ consts, unsigned int n_consts, unsigned int n_slots) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [2][kChunk] instruction words | staging tile (3*B*P bytes, 16-aligned) | constants | slots
     uint64_t* code_s = reinterpret_cast<uint64_t*>(smem_raw);
@@ -55,7 +55,9 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
 
     const unsigned int first = blockIdx.x * B * P;
     double acc[P], va[P], vb[P];
-    double out_r[P], out_g[P], out_b[P];
+    // channel values go to three extra slots (n_slots .. n_slots+2): keeping them in registers makes the
+    // compiler copy them at every handler join
+    double* outs = slots + (size_t)n_slots * P * B + tid;
 #pragma unroll
     for (int k = 0; k < P; k++) {
         unsigned int j = first + k * B + tid;
@@ -64,7 +66,7 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
         unsigned int xi = pix - yi * p.W;
         slots[(0 * P + k) * B + tid] = (double)xi;      // `x as f64`, reference src/render.rs:25
         slots[(1 * P + k) * B + tid] = (double)yi;
-        acc[k] = 0.0; va[k] = 0.0; vb[k] = 0.0; out_r[k] = 0.0; out_g[k] = 0.0; out_b[k] = 0.0;
+        acc[k] = 0.0; va[k] = 0.0; vb[k] = 0.0;
     }
     for (unsigned int i = tid; i < n_consts; i += B) consts_s[i] = consts[i];
 
@@ -103,6 +105,7 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
         const unsigned int cnt = (n_instr - c * kChunk < (unsigned)kChunk) ? (n_instr - c * kChunk) : (unsigned)kChunk;
         uint64_t w = cs[0];
         fetch(w, va, vb);                                  // the chunk's first instruction: not overlapped
+#pragma unroll 2
         for (unsigned int i = 0; i < cnt; i++) {
             // ---- stage 1: next instruction's word and operands (overlaps stage 2) -----------------
             const uint64_t wn = cs[i + 1 < cnt ? i + 1 : i];
@@ -172,17 +175,9 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
 #pragma unroll
                     for (int k = 0; k < P; k++) acc[k] = mr_tex(t.data, t.w, t.h, imm & 3u, x[k], y[k]);
                 } break;
-                case BC_OUT_R:
+                case BC_OUT_R: case BC_OUT_G: case BC_OUT_B:
 #pragma unroll
-                    for (int k = 0; k < P; k++) out_r[k] = x[k];
-                    break;
-                case BC_OUT_G:
-#pragma unroll
-                    for (int k = 0; k < P; k++) out_g[k] = x[k];
-                    break;
-                case BC_OUT_B:
-#pragma unroll
-                    for (int k = 0; k < P; k++) out_b[k] = x[k];
+                    for (int k = 0; k < P; k++) outs[((op - BC_OUT_R) * P + k) * B] = x[k];
                     break;
                 default: break;   // BC_END
                 }
@@ -202,14 +197,15 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
 #pragma unroll
     for (int k = 0; k < P; k++) {
         unsigned int l = k * B + tid;   // pixel within the block
-        stage[3u * l + 0u] = (unsigned char)mr_as_u8(out_r[k]);
-        stage[3u * l + 1u] = (unsigned char)mr_as_u8(out_g[k]);
-        stage[3u * l + 2u] = (unsigned char)mr_as_u8(out_b[k]);
+        const double o_r = outs[(0 * P + k) * B], o_g = outs[(1 * P + k) * B], o_b = outs[(2 * P + k) * B];
+        stage[3u * l + 0u] = (unsigned char)mr_as_u8(o_r);
+        stage[3u * l + 1u] = (unsigned char)mr_as_u8(o_g);
+        stage[3u * l + 2u] = (unsigned char)mr_as_u8(o_b);
         unsigned int j = first + l;
         if (p.f64_out != nullptr && j < p.n) {
-            p.f64_out[j] = out_r[k];
-            p.f64_out[(size_t)p.f64_plane + j] = out_g[k];
-            p.f64_out[2u * (size_t)p.f64_plane + j] = out_b[k];
+            p.f64_out[j] = o_r;
+            p.f64_out[(size_t)p.f64_plane + j] = o_g;
+            p.f64_out[2u * (size_t)p.f64_plane + j] = o_b;
         }
     }
     __syncthreads();
@@ -227,7 +223,7 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
 size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_slots, unsigned int n_consts) {
     size_t stage = (3u * (size_t)block * pixels_per_thread + 15u) & ~size_t(15);
     return 2 * kChunk * sizeof(uint64_t) + stage + (size_t)((n_consts + 1u) & ~1u) * sizeof(double) +
-           (size_t)n_slots * pixels_per_thread * block * sizeof(double);
+           (size_t)(n_slots + 3u) * pixels_per_thread * block * sizeof(double);   // + 3 channel-output slots
 }
 
 cudaError_t launch_interp(const MrParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
@@ -242,17 +238,17 @@ cudaError_t launch_interp(const MrParams& p, const uint64_t* d_code, unsigned in
     case 1:
         e = cudaFuncSetAttribute(maray_interp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        maray_interp<1><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts);
+        maray_interp<1><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_slots);
         break;
     case 2:
         e = cudaFuncSetAttribute(maray_interp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        maray_interp<2><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts);
+        maray_interp<2><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_slots);
         break;
     case 4:
         e = cudaFuncSetAttribute(maray_interp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        maray_interp<4><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts);
+        maray_interp<4><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_slots);
         break;
     default: return cudaErrorInvalidValue;
     }
