@@ -1,0 +1,63 @@
+"""The command-line front end (maray_b200/maray_cuda), shaped like the reference's examples/maray.rs:
+`-i scene.maray -o out.png [-t textures...]`.  PNG input/output goes through the built-in codec."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from maray_b200 import expr as E
+from maray_b200 import scenes
+from oracle.oracle import OracleScene
+
+from conftest import ROOT
+
+CLI = os.path.join(ROOT, "maray_b200", "maray_cuda")
+
+
+def test_cli_usage_and_no_cpu_fallback(tmp_path):
+    assert os.path.exists(CLI), "build with make -C maray_b200/csrc"
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: maray_cuda -i" in r.stderr
+    scene = tmp_path / "s.maray"
+    scene.write_bytes(scenes.sdf(32, 16, 3))
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([CLI, "-c", "8", "-i", str(scene), "-o", str(tmp_path / "o.png")], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr and not (tmp_path / "o.png").exists()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("backend", ["nvrtc", "interp"])
+def test_cli_renders_textured_scene_like_the_oracle(tmp_path, backend):
+    """Textures in four PNG flavours (RGB, RGBA, palette, 16-bit grey) must load as image::open().to_rgb8()
+    would, and the written PNG must decode to the oracle's bytes."""
+    rgb = scenes.synthetic_textures(1, 32)[0]
+    files, arrays = [], []
+    for i, mode in enumerate(["RGB", "RGBA", "P", "I;16"]):
+        path = str(tmp_path / f"t{i}.png")
+        if mode == "RGB":
+            Image.fromarray(rgb).save(path); arr = rgb
+        elif mode == "RGBA":
+            rgba = np.dstack([rgb[::-1], np.full(rgb.shape[:2], 77, np.uint8)])
+            Image.fromarray(rgba, "RGBA").save(path); arr = rgb[::-1]
+        elif mode == "P":
+            pal = Image.fromarray(rgb).quantize(16)
+            pal.save(path); arr = np.array(pal.convert("RGB"))
+        else:
+            g16 = (rgb[:, :, 0].astype(np.uint16) << 8) | 0x5A
+            Image.fromarray(g16).save(path); arr = np.repeat((g16 >> 8).astype(np.uint8)[:, :, None], 3, axis=2)
+        files.append(path); arrays.append(arr)
+    x, y = E.x(), E.y()
+    color = [E.app(E.channel(0, 0), x, y), E.add(E.app(E.channel(1, 1), x, y), E.app(E.channel(2, 2), y, x)),
+             E.app(E.channel(3, 0), E.div(x, E.nat(2)), E.div(y, E.nat(2)))]
+    scene_bytes = E.to_bytes([48, 40], color)
+    scene = tmp_path / "s.maray"
+    scene.write_bytes(scene_bytes)
+    out = str(tmp_path / "out.png")
+    r = subprocess.run([CLI, "-c", "8", "-i", str(scene), "-o", out, "-b", backend, "-t"] + files, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.array(Image.open(out).convert("RGB"))
+    want = OracleScene(scene_bytes, arrays).render()
+    assert np.array_equal(got, want)
