@@ -96,10 +96,9 @@ def chess_4k() -> bytes:
     return chess_resampled(3840, 2160)
 
 
-def chess_dsl(w: int = 1024, h: int = 1024, cells: int = 8) -> bytes:
-    """examples/chess.rs re-run through the builder at size [w, h] (reference examples/chess.rs:5-50),
-    WITHOUT `simplify`/`compress` (those are content-time rewrites that change float results and are
-    not restated yet); sharing is put on the wire with `share_let`."""
+def chess_shape(w: int = 1024, h: int = 1024, cells: int = 8) -> E.Expr:
+    """The `shape` expression of examples/chess.rs at size [w, h], as built by lines 8-39 of that file
+    (before `simplify`/`compress`)."""
     fx, fy = E.div(E.x(), E.nat(w)), E.div(E.y(), E.nat(h))
     p = [fx, fy]
     texture = E.set_unit_square(E.chess(8))
@@ -118,7 +117,15 @@ def chess_dsl(w: int = 1024, h: int = 1024, cells: int = 8) -> bytes:
             get_uv2 = texture.subst2(E.to_uv(tri2, uv2, xy))
             shape2 = E.mul(E.inside_triangle(tri2, xy), get_uv2).subst2(p)
             shape = E.set_or(shape, E.set_or(shape1, shape2))
-    ch = E.mul(shape, E.nat(255))
+    return shape
+
+
+def chess_dsl(w: int = 1024, h: int = 1024, cells: int = 8) -> bytes:
+    """examples/chess.rs re-run through the builder at size [w, h] (reference examples/chess.rs:5-50),
+    WITHOUT `simplify`/`compress`: HEAD's `simplify` does not terminate on this scene
+    (maray_b200/simplify.py `SimplifyDiverges`, tests/test_simplify.py), so the shipped file cannot be
+    regenerated from HEAD; sharing is put on the wire with `share_let`."""
+    ch = E.mul(chess_shape(w, h, cells), E.nat(255))
     return E.to_bytes([w, h], E.share_let([ch, ch, ch]))
 
 
