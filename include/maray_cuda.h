@@ -70,10 +70,15 @@ typedef struct maray_cuda_stats {
     uint32_t jit_registers;       /* registers per thread of the generated kernel (0 = unknown)      */
     uint32_t jit_source_bytes;
     uint32_t jit_cubin_bytes;
+    uint32_t jit_units;           /* translation units compiled (1, or 1 + segments when linked)     */
+    uint32_t jit_compile_threads; /* host threads that ran NVRTC concurrently (0 on a cache hit)     */
+    uint32_t jit_cache_hit;       /* 1 when the cubin came from the MARAY_JIT_CACHE directory        */
+    uint32_t reserved0;
     /* timings, milliseconds */
     double lower_ms;              /* Expr -> SSA                                                     */
     double codegen_ms;            /* SSA -> source / bytecode                                        */
-    double nvrtc_ms;              /* NVRTC compile (reported separately from render time)            */
+    double nvrtc_ms;              /* NVRTC compile incl. link (reported separately from render time) */
+    double link_ms;               /* nvJitLink share of nvrtc_ms (0 for a single translation unit)   */
     double load_ms;               /* cubin load + uploads                                            */
     double kernel_ms[8];          /* last render: device time of the band kernel, per GPU            */
     double gather_ms;             /* last render: band gather to GPU 0 (peer copies)                 */

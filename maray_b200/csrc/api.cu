@@ -6,15 +6,18 @@
 //   local band buffer and push it into GPU 0's frame with one peer copy (the only exchange step);
 //   one device->host copy hands the frame to the caller.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <nvrtc.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/maray_cuda.h"
@@ -72,12 +75,15 @@ struct maray_cuda {
     Program prog;
     bool compiled = false;
     int backend = -1;
-    std::string source;
+    std::string source;                 // the kernel's translation unit (== modules[0])
+    std::vector<std::string> modules;   // every translation unit of the last NVRTC compile
     std::vector<char> cubin;
     Bytecode bc;
     unsigned interp_block = 128, interp_ppt = 2;
     unsigned jit_block = 256;
+    unsigned jit_dyn_smem = 0;                         // dynamic shared memory of the generated kernel
     unsigned jit_maxreg = 0;
+    unsigned jit_link_maxreg = 0;                      // register cap of separately compiled segment functions
     unsigned jit_ncol = 0, jit_nrow = 0;               // hoisted values per column / per row
     maray_cuda_stats stats{};
     int report_kind = MARAY_REPORT_NONE;
@@ -169,49 +175,260 @@ void fill_program_stats(maray_cuda* h) {
     s.legacy_layout = h->scene.legacy_layout ? 1 : 0;
 }
 
-// NVRTC: source -> sm_100a cubin.  Works without a GPU.
-int nvrtc_compile(maray_cuda* h) {
+// ---- NVRTC: source -> sm_100a cubin.  Works without a GPU. ----------------------------------------
+//
+// One translation unit is compiled straight to a cubin.  Several (generate_cuda_modules: the kernel's
+// unit plus one unit per segment function) are compiled concurrently, one NVRTC program per host
+// thread, with --relocatable-device-code, and linked into one cubin by nvJitLink.  The finished
+// cubin can be kept in a directory (MARAY_JIT_CACHE) keyed by the generated text and the options.
+
+// nvJitLink is bound at run time, by path: a process that already holds another libnvJitLink.so.12
+// (PyTorch bundles its own, one minor version older than this toolkit's) would otherwise hand that
+// one to us, and a linker older than the compiler that produced the objects is not supported.  The
+// `_12_0` entry points exist in every 12.x release.
+struct JitLink {
+    typedef int (*create_fn)(void**, uint32_t, const char**);
+    typedef int (*destroy_fn)(void**);
+    typedef int (*add_fn)(void*, int, const void*, size_t, const char*);
+    typedef int (*complete_fn)(void*);
+    typedef int (*size_fn)(void*, size_t*);
+    typedef int (*get_fn)(void*, void*);
+    typedef int (*getlog_fn)(void*, char*);
+    create_fn create = nullptr; destroy_fn destroy = nullptr; add_fn add = nullptr; complete_fn complete = nullptr;
+    size_fn cubin_size = nullptr; get_fn cubin = nullptr; size_fn log_size = nullptr; getlog_fn log = nullptr;
+    std::string where;
+    static constexpr int kInputCubin = 1;   // NVJITLINK_INPUT_CUBIN
+
+    static const JitLink* get() {
+        static const JitLink* inst = [] () -> const JitLink* {
+            std::vector<std::string> paths;
+            if (const char* e = std::getenv("MARAY_NVJITLINK")) paths.push_back(e);
+            if (const char* e = std::getenv("CUDA_HOME")) paths.push_back(std::string(e) + "/lib64/libnvJitLink.so.12");
+            paths.push_back("/usr/local/cuda/lib64/libnvJitLink.so.12");
+            paths.push_back("libnvJitLink.so.12");
+            for (const std::string& p : paths) {
+                void* so = dlopen(p.c_str(), RTLD_NOW | RTLD_LOCAL);
+                if (!so) continue;
+                JitLink* j = new JitLink;
+                j->create = reinterpret_cast<create_fn>(dlsym(so, "__nvJitLinkCreate_12_0"));
+                j->destroy = reinterpret_cast<destroy_fn>(dlsym(so, "__nvJitLinkDestroy_12_0"));
+                j->add = reinterpret_cast<add_fn>(dlsym(so, "__nvJitLinkAddData_12_0"));
+                j->complete = reinterpret_cast<complete_fn>(dlsym(so, "__nvJitLinkComplete_12_0"));
+                j->cubin_size = reinterpret_cast<size_fn>(dlsym(so, "__nvJitLinkGetLinkedCubinSize_12_0"));
+                j->cubin = reinterpret_cast<get_fn>(dlsym(so, "__nvJitLinkGetLinkedCubin_12_0"));
+                j->log_size = reinterpret_cast<size_fn>(dlsym(so, "__nvJitLinkGetErrorLogSize_12_0"));
+                j->log = reinterpret_cast<getlog_fn>(dlsym(so, "__nvJitLinkGetErrorLog_12_0"));
+                if (j->create && j->destroy && j->add && j->complete && j->cubin_size && j->cubin && j->log_size && j->log) {
+                    j->where = p;
+                    return j;
+                }
+                delete j;
+                dlclose(so);
+            }
+            return nullptr;
+        }();
+        return inst;
+    }
+};
+
+struct UnitResult {
+    nvrtcResult rc = NVRTC_SUCCESS;
+    std::vector<char> cubin;
+    std::string log;
+    uint32_t max_registers = 0;   // largest "Used N registers" in the ptxas -v log of the unit
+};
+
+void compile_unit(const std::string& source, const std::vector<std::string>& options, UnitResult* out) {
     nvrtcProgram prog;
-    if (nvrtcCreateProgram(&prog, h->source.c_str(), "maray_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
-        return fail(h, MARAY_E_COMPILE, "nvrtcCreateProgram failed");
-    std::vector<const char*> opts = {
+    out->rc = nvrtcCreateProgram(&prog, source.c_str(), "maray_jit.cu", 0, nullptr, nullptr);
+    if (out->rc != NVRTC_SUCCESS) return;
+    std::vector<const char*> opts;
+    for (const std::string& o : options) opts.push_back(o.c_str());
+    out->rc = nvrtcCompileProgram(prog, int(opts.size()), opts.data());
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    out->log.assign(log_size, '\0');
+    if (log_size > 1) nvrtcGetProgramLog(prog, &out->log[0]);
+    if (out->rc == NVRTC_SUCCESS) {
+        size_t n = 0;
+        if (nvrtcGetCUBINSize(prog, &n) == NVRTC_SUCCESS && n) {
+            out->cubin.resize(n);
+            nvrtcGetCUBIN(prog, out->cubin.data());
+        } else {
+            out->rc = NVRTC_ERROR_INTERNAL_ERROR;
+        }
+    }
+    nvrtcDestroyProgram(&prog);
+    for (size_t at = out->log.find("Used "); at != std::string::npos; at = out->log.find("Used ", at + 5)) {
+        uint32_t r = uint32_t(std::atoi(out->log.c_str() + at + 5));
+        if (out->log.compare(at + 5 + std::to_string(r).size(), 10, " registers") == 0 && r > out->max_registers)
+            out->max_registers = r;
+    }
+}
+
+// 128-bit FNV-1a style key over the generated text and the compile options.
+std::string cache_key(const std::vector<std::string>& modules, const std::vector<std::string>& options) {
+    uint64_t a = 0xcbf29ce484222325ull, b = 0x84222325cbf29ce4ull;
+    auto mix = [&](const std::string& t) {
+        for (unsigned char c : t) {
+            a = (a ^ c) * 0x100000001b3ull;
+            b = (b ^ (c + 0x9e)) * 0x00000100000001b5ull;
+        }
+        a = (a ^ 0xff) * 0x100000001b3ull;
+        b = (b ^ 0xfe) * 0x00000100000001b5ull;
+    };
+    for (const std::string& m : modules) mix(m);
+    for (const std::string& o : options) mix(o);
+    int major = 0, minor = 0;
+    nvrtcVersion(&major, &minor);
+    mix("nvrtc " + std::to_string(major) + "." + std::to_string(minor) + " " + maray_cuda_version());
+    char buf[40];
+    std::snprintf(buf, sizeof buf, "%016llx%016llx", (unsigned long long)a, (unsigned long long)b);
+    return buf;
+}
+
+struct CacheHeader { char magic[8]; uint32_t registers; uint32_t units; uint64_t cubin_bytes; };
+const char kCacheMagic[8] = {'M', 'R', 'C', 'U', 'B', 'I', 'N', '1'};
+
+bool cache_load(const std::string& path, std::vector<char>* cubin, uint32_t* registers) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    CacheHeader hd;
+    bool ok = std::fread(&hd, sizeof hd, 1, f) == 1 && std::memcmp(hd.magic, kCacheMagic, 8) == 0 &&
+              hd.cubin_bytes > 0 && hd.cubin_bytes < (1ull << 32);
+    if (ok) {
+        cubin->resize(size_t(hd.cubin_bytes));
+        ok = std::fread(cubin->data(), 1, cubin->size(), f) == cubin->size();
+        *registers = hd.registers;
+    }
+    std::fclose(f);
+    return ok;
+}
+
+void cache_store(const std::string& path, const std::vector<char>& cubin, uint32_t registers, uint32_t units) {
+    std::string tmp = path + ".tmp" + std::to_string((unsigned long long)now_ms());
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    CacheHeader hd;
+    std::memcpy(hd.magic, kCacheMagic, 8);
+    hd.registers = registers; hd.units = units; hd.cubin_bytes = cubin.size();
+    bool ok = std::fwrite(&hd, sizeof hd, 1, f) == 1 && std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    ok = (std::fclose(f) == 0) && ok;
+    if (ok) ok = std::rename(tmp.c_str(), path.c_str()) == 0;   // atomic: readers never see a partial file
+    if (!ok) std::remove(tmp.c_str());
+}
+
+int nvrtc_compile(maray_cuda* h) {
+    const size_t n_units = h->modules.size();
+    const bool link = n_units > 1;
+    std::vector<std::string> options = {
         "--gpu-architecture=sm_100a",
         "--fmad=false",               // the reference never fuses a*b+c
         "--std=c++17",
-        "-lineinfo",
         "--ptxas-options=-v",
     };
-    std::string maxreg = "--maxrregcount=" + std::to_string(h->jit_maxreg);
-    if (h->jit_maxreg) opts.push_back(maxreg.c_str());
+    // Line tables map SASS to the generated text (ncu source page).  On by default for one unit; a
+    // linked build carries one table per unit (4x the cubin, seconds of link time): MARAY_JIT_LINEINFO=1.
+    bool lineinfo = !link;
+    if (const char* e = std::getenv("MARAY_JIT_LINEINFO")) lineinfo = std::strtoul(e, nullptr, 10) != 0;
+    if (lineinfo) options.push_back("-lineinfo");
+    // A separately compiled segment function does not see the kernel's __launch_bounds__: it needs the
+    // register cap spelled out, or the linked kernel inherits a larger count than the launch shape allows.
+    unsigned maxreg = h->jit_maxreg ? h->jit_maxreg : (link ? h->jit_link_maxreg : 0);
+    if (maxreg) options.push_back("--maxrregcount=" + std::to_string(maxreg));
+    if (link) options.push_back("--relocatable-device-code=true");
+    if (std::getenv("MARAY_JIT_NOSLOW")) options.push_back("-DMR_NO_SLOW=1");   // experiment only (wrong for huge/NaN arguments)
     if (const char* e = std::getenv("MARAY_LIBM"))      // A/B: MARAY_LIBM=cuda uses libdevice's sin/exp/log
-        if (std::string(e) == "cuda") opts.push_back("-DMR_LIBM_PLAIN=1");
-    nvrtcResult rc = nvrtcCompileProgram(prog, int(opts.size()), opts.data());
-    size_t log_size = 0;
-    nvrtcGetProgramLogSize(prog, &log_size);
-    std::string log(log_size, '\0');
-    if (log_size > 1) nvrtcGetProgramLog(prog, &log[0]);
-    if (rc != NVRTC_SUCCESS) {
-        nvrtcDestroyProgram(&prog);
-        if (log.size() > 4000) log.resize(4000);
-        return fail(h, MARAY_E_COMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(rc) + "\n" + log);
-    }
-    size_t cubin_size = 0;
-    if (nvrtcGetCUBINSize(prog, &cubin_size) != NVRTC_SUCCESS || cubin_size == 0) {
-        nvrtcDestroyProgram(&prog);
-        return fail(h, MARAY_E_COMPILE, "NVRTC produced no cubin");
-    }
-    h->cubin.resize(cubin_size);
-    nvrtcGetCUBIN(prog, h->cubin.data());
-    nvrtcDestroyProgram(&prog);
-    // registers of the kernel from the ptxas -v log:
-    //   "Function properties for maray_jit" ... "Used N registers"
+        if (std::string(e) == "cuda") options.push_back("-DMR_LIBM_PLAIN=1");
+
     h->stats.jit_registers = 0;
-    size_t at = log.find(std::string("Function properties for ") + kJitKernelName);
-    if (at != std::string::npos) {
-        size_t u = log.find("Used ", at);
-        if (u != std::string::npos) h->stats.jit_registers = uint32_t(std::atoi(log.c_str() + u + 5));
+    h->stats.jit_units = uint32_t(n_units);
+    h->stats.jit_compile_threads = 0;
+    h->stats.jit_cache_hit = 0;
+    h->stats.link_ms = 0.0;
+
+    std::string cache_path;
+    if (const char* dir = std::getenv("MARAY_JIT_CACHE")) {
+        if (*dir) {
+            cache_path = std::string(dir) + "/" + cache_key(h->modules, options) + ".mrcubin";
+            uint32_t regs = 0;
+            if (cache_load(cache_path, &h->cubin, &regs)) {
+                h->stats.jit_registers = regs;
+                h->stats.jit_cache_hit = 1;
+                return MARAY_OK;
+            }
+        }
     }
-    if (std::getenv("MARAY_JIT_VERBOSE")) std::fprintf(stderr, "%s\n", log.c_str());
+
+    std::vector<UnitResult> res(n_units);
+    unsigned n_threads = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("MARAY_JIT_THREADS")) n_threads = unsigned(std::strtoul(e, nullptr, 10));
+    n_threads = std::max(1u, std::min<unsigned>(n_threads, unsigned(n_units)));
+    h->stats.jit_compile_threads = n_threads;
+    if (n_threads == 1) {
+        for (size_t i = 0; i < n_units; i++) compile_unit(h->modules[i], options, &res[i]);
+    } else {
+        // the kernel's unit is small; the segment units are roughly equal: a shared counter balances them
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < n_threads; t++)
+            pool.emplace_back([&] {
+                for (size_t i = next.fetch_add(1); i < n_units; i = next.fetch_add(1)) compile_unit(h->modules[i], options, &res[i]);
+            });
+        for (std::thread& t : pool) t.join();
+    }
+    for (size_t i = 0; i < n_units; i++) {
+        if (res[i].rc != NVRTC_SUCCESS) {
+            std::string log = res[i].log;
+            if (log.size() > 4000) log.resize(4000);
+            return fail(h, MARAY_E_COMPILE, "NVRTC (unit " + std::to_string(i) + "): " + nvrtcGetErrorString(res[i].rc) + "\n" + log);
+        }
+        h->stats.jit_registers = std::max(h->stats.jit_registers, res[i].max_registers);
+        if (std::getenv("MARAY_JIT_VERBOSE")) std::fprintf(stderr, "%s\n", res[i].log.c_str());
+    }
+
+    if (!link) {
+        h->cubin = std::move(res[0].cubin);
+        // registers of the kernel from the ptxas -v log:
+        //   "Function properties for maray_jit" ... "Used N registers"
+        const std::string& log = res[0].log;
+        size_t at = log.find(std::string("Function properties for ") + kJitKernelName);
+        if (at != std::string::npos) {
+            size_t u = log.find("Used ", at);
+            if (u != std::string::npos) h->stats.jit_registers = uint32_t(std::atoi(log.c_str() + u + 5));
+        }
+    } else {
+        double t0 = now_ms();
+        const JitLink* J = JitLink::get();
+        if (!J) return fail(h, MARAY_E_COMPILE, "libnvJitLink.so.12 not found (set MARAY_NVJITLINK, or MARAY_JIT_PARALLEL=0)");
+        void* lk = nullptr;
+        const char* lopts[] = {"-arch=sm_100a", "-lineinfo"};
+        if (J->create(&lk, lineinfo ? 2 : 1, lopts) != 0) return fail(h, MARAY_E_COMPILE, "nvJitLinkCreate failed");
+        auto link_error = [&](const char* what) {
+            size_t n = 0;
+            std::string log;
+            if (J->log_size(lk, &n) == 0 && n > 1) { log.assign(n, '\0'); J->log(lk, &log[0]); }
+            J->destroy(&lk);
+            if (log.size() > 4000) log.resize(4000);
+            return fail(h, MARAY_E_COMPILE, std::string("nvJitLink: ") + what + "\n" + log);
+        };
+        for (size_t i = 0; i < n_units; i++) {
+            std::string name = "maray_unit" + std::to_string(i);
+            if (J->add(lk, JitLink::kInputCubin, res[i].cubin.data(), res[i].cubin.size(), name.c_str()) != 0)
+                return link_error("adding a unit failed");
+        }
+        if (J->complete(lk) != 0) return link_error("link failed");
+        size_t n = 0;
+        if (J->cubin_size(lk, &n) != 0 || n == 0) return link_error("no linked cubin");
+        h->cubin.resize(n);
+        if (J->cubin(lk, h->cubin.data()) != 0) return link_error("reading the linked cubin failed");
+        J->destroy(&lk);
+        h->stats.link_ms = now_ms() - t0;
+        // The linked kernel's register count is that of its call graph; without a device to ask
+        // (maray_cuda_compile refines this after the load) the cap is what is known.
+        if (maxreg) h->stats.jit_registers = maxreg;
+    }
+    if (!cache_path.empty()) cache_store(cache_path, h->cubin, h->stats.jit_registers, uint32_t(n_units));
     return MARAY_OK;
 }
 
@@ -278,7 +495,7 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
         }
         void* args[] = {&p};
         unsigned grid = (n + h->jit_block - 1) / h->jit_block;
-        CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, 0, stream));
+        CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, h->jit_dyn_smem, stream));
     } else {
         CU_TRY(h, launch_interp(p, g.d_code, unsigned(h->bc.code.size()), g.d_consts, unsigned(h->bc.consts.size()),
                                 h->bc.n_slots, h->interp_block, h->interp_ppt, stream));
@@ -516,13 +733,38 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         if (const char* e = std::getenv("MARAY_JIT_SYNC_EVERY")) copt.sync_every = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_CONST_BANK")) copt.constants_in_bank = std::strtoul(e, nullptr, 10) != 0;
         if (const char* e = std::getenv("MARAY_JIT_HOIST")) copt.hoist = std::strtoul(e, nullptr, 10) != 0;
+        if (const char* e = std::getenv("MARAY_JIT_SCRATCH")) copt.scratch_batches = std::strtoul(e, nullptr, 10) != 0;
+        if (const char* e = std::getenv("MARAY_JIT_BATCH_WIDTH")) copt.batch_width = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_BLOCK")) copt.block = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10));
         h->jit_maxreg = 0;
         if (const char* e = std::getenv("MARAY_JIT_MAXREG")) h->jit_maxreg = unsigned(std::strtoul(e, nullptr, 10));
-        h->source = generate_cuda_source(h->prog, copt, &info);
+        // MARAY_JIT_PARALLEL=1: every segment function becomes its own translation unit, the units are
+        // compiled on all host cores and linked (nvrtc_compile) -- 3-5x less compile latency on large
+        // programs, but a separately compiled segment has to honour the full call ABI and the kernel
+        // runs ~20 % slower (measured on the 20 000-value deep scene: 17.6 vs 14.7 ms), so one unit is
+        // the default and MARAY_JIT_CACHE is the answer to compile latency.
+        // sin/exp/ln stay out of line above the threshold: inlined, the code
+        // of a transcendental-heavy program is several MB of instructions no warp ever re-uses, and the
+        // kernel becomes instruction-fetch bound (measured: 33.8 ms inlined vs 18.7 ms out of line on
+        // the 20 000-value deep scene, no_instruction stalls 9.1 per issued instruction; profiles/).
+        bool parallel = false;
+        if (const char* e = std::getenv("MARAY_JIT_PARALLEL")) parallel = std::strtoul(e, nullptr, 10) != 0;
+        if (parallel) {
+            copt.separate_segments = true;
+            if (!std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = 8192;
+        }
+        h->modules = generate_cuda_modules(h->prog, copt, &info);
+        h->jit_link_maxreg = info.max_registers;
+        if (h->modules.size() > 1) {
+            CodegenInfo unused;
+            h->source = generate_cuda_source(h->prog, copt, &unused);   // the same statements as ONE unit (tooling, tests)
+        } else {
+            h->source = h->modules[0];
+        }
         h->stats.codegen_ms = now_ms() - t1;
         h->jit_block = info.block;
+        h->jit_dyn_smem = info.dynamic_smem_bytes;
         h->jit_ncol = info.n_col;
         h->jit_nrow = info.n_row;
         h->stats.jit_segments = info.segments;
@@ -558,6 +800,9 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
             if (backend == MARAY_BACKEND_NVRTC) {
                 CU_TRY(h, cudaLibraryLoadData(&g.lib, h->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
                 CU_TRY(h, cudaLibraryGetKernel(&g.jit_kernel, g.lib, kJitKernelName));
+                cudaFuncAttributes fa;
+                if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(g.jit_kernel)) == cudaSuccess) h->stats.jit_registers = uint32_t(fa.numRegs);
+                else cudaGetLastError();
                 if (h->jit_ncol || h->jit_nrow) {
                     CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_x, g.lib, kJitPreXName));
                     CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_y, g.lib, kJitPreYName));

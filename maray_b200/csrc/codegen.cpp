@@ -32,6 +32,8 @@ void append_const(std::string& s, double v) {
     s += buf;
 }
 
+constexpr uint32_t kScratchRows = 8;   // argument rows of the batched sin/exp/ln scratch (as many result rows follow)
+
 struct Emitter {
     const Program& P;
     bool inline_trans;
@@ -39,6 +41,7 @@ struct Emitter {
     // In the per-pixel kernel a hoisted value is a load from its table: 1 = column table, 2 = row table.
     const std::vector<uint8_t>* load_kind = nullptr;
     const std::vector<uint32_t>* table_index = nullptr;
+    bool scratch_batches = false;
 
     void operand(std::string& s, uint32_t id) const {
         const Node& n = P.nodes[id];
@@ -63,6 +66,26 @@ struct Emitter {
     void batch_calls(std::string& s, const std::vector<uint32_t>& order, size_t i, size_t j) const {
         const char* fn = P.nodes[order[i]].op == OP_SIN ? "sin" : (P.nodes[order[i]].op == OP_EXP ? "exp" : "log");
         char buf[96];
+        if (scratch_batches) {
+            // arguments -> this thread's scratch rows, one leaf call for the whole batch, results back
+            // (rows: kScratchRows; lower.cpp's kBatchMax never exceeds it)
+            while (i < j) {
+                const size_t k = std::min<size_t>(j - i, kScratchRows);
+                if (k == 1) { statement(s, order[i]); i++; continue; }
+                for (size_t m = 0; m < k; m++) {
+                    std::snprintf(buf, sizeof buf, "  MR_S(%zu) = ", m);
+                    s += buf; operand(s, P.nodes[order[i + m]].a); s += ";\n";
+                }
+                std::snprintf(buf, sizeof buf, "  if (mr_%s_batch(%zuu)) mr_%s_fix(%zuu);\n", fn, k, fn, k);
+                s += buf;
+                for (size_t m = 0; m < k; m++) {
+                    std::snprintf(buf, sizeof buf, "  const double v%u = MR_R(%zu);\n", order[i + m], m);
+                    s += buf;
+                }
+                i += k;
+            }
+            return;
+        }
         while (i < j) {
             size_t k = (j - i >= 4) ? 4 : ((j - i >= 2) ? 2 : 1);
             if (k == 1) { statement(s, order[i]); i++; continue; }
@@ -122,7 +145,10 @@ struct Emitter {
 
 }  // namespace
 
-std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt, CodegenInfo* info) {
+namespace {
+// Common generator.  modules[0] always holds the kernel; with opt.separate_segments (and a segmented
+// program) every segment function is its own translation unit in modules[1..].
+std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt, CodegenInfo* info) {
     // The per-pixel kernel evaluates the values that depend on both x and y; x-only / y-only frontier
     // values are loaded from the column / row tables (each at its first use), the x-only / y-only
     // values behind them are evaluated by the two prologue kernels only.
@@ -181,11 +207,22 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
     const bool segmented = order.size() > seg_len;
     const uint32_t n_seg = segmented ? uint32_t((order.size() + seg_len - 1) / seg_len) : 1;
 
+    const bool split = opt.separate_segments && segmented;
+    const uint32_t block = opt.block ? ((opt.block + 31) / 32) * 32 : 256;
+    const bool use_batches = !em.inline_trans;
+    const bool scratch = use_batches && opt.scratch_batches;
+    em.scratch_batches = scratch;
+    std::string prelude = "// generated by maray_b200 (NVRTC back end); compiled with --fmad=false\n";
+    if (scratch) {
+        prelude += "#define MR_SCR_STRIDE " + std::to_string(block) + "\n";
+        prelude += "#define MR_BATCH_WIDTH " + std::to_string(opt.batch_width == 4 ? 4 : 2) + "\n";
+    }
+    prelude += kDeviceSemText;
+    prelude += "\n";
     std::string src;
     src.reserve(order.size() * 40 + 8192);
-    src += "// generated by maray_b200 (NVRTC back end); compiled with --fmad=false\n";
-    src += kDeviceSemText;
-    src += "\n";
+    src += prelude;
+    std::string bank_extern;   // what a separately compiled segment needs to see of the constant table
     if (!bank.empty()) {
         src += "__constant__ unsigned long long MRK_BITS[" + std::to_string(bank.size()) + "] = {\n";
         char kb[32];
@@ -194,8 +231,11 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
             src += kb;
         }
         src += "};\n#define MRK(i) (reinterpret_cast<const double*>(MRK_BITS)[i])\n";
+        bank_extern = "extern __constant__ unsigned long long MRK_BITS[" + std::to_string(bank.size()) +
+                      "];\n#define MRK(i) (reinterpret_cast<const double*>(MRK_BITS)[i])\n";
     }
-    const bool use_batches = !em.inline_trans;
+    std::vector<std::string> modules;   // modules[0] is filled in at the end
+    modules.emplace_back();
     char buf[256];
     uint32_t frame_slots = 0;
     std::vector<int32_t> slot(prog.nodes.size(), -1);
@@ -242,11 +282,23 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
 
         for (uint32_t s = 0; s < n_seg; s++) {
             size_t lo = size_t(s) * seg_len, hi = std::min(order.size(), lo + seg_len);
-            std::snprintf(buf, sizeof buf,
-                          "__device__ __noinline__ void mr_seg%u(double* __restrict__ F, const double X, const double Y, "
-                          "const MrTexture* __restrict__ T, const double* __restrict__ CV, const unsigned int CW, "
-                          "const double* __restrict__ RV, const unsigned int RW) {\n", s);
-            src += buf;
+            static const char* const kSegArgs =
+                "(double* __restrict__ F, const double X, const double Y, const MrTexture* __restrict__ T, "
+                "const double* __restrict__ CV, const unsigned int CW, const double* __restrict__ RV, const unsigned int RW)";
+            std::string seg_text;
+            std::string& out = split ? seg_text : src;
+            if (split) {
+                // declaration for the kernel's translation unit; the definition gets its own
+                std::snprintf(buf, sizeof buf, "extern __device__ void mr_seg%u", s);
+                src += buf; src += kSegArgs; src += ";\n";
+                seg_text.reserve((hi - lo) * 48 + prelude.size() + 1024);
+                seg_text += prelude;
+                seg_text += bank_extern;
+                std::snprintf(buf, sizeof buf, "__device__ void mr_seg%u", s);
+            } else {
+                std::snprintf(buf, sizeof buf, "__device__ __noinline__ void mr_seg%u", s);
+            }
+            out += buf; out += kSegArgs; out += " {\n";
             // imports: values defined in earlier segments and read here
             std::vector<uint32_t> imports;
             {
@@ -267,28 +319,28 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
             }
             for (uint32_t id : imports) {
                 std::snprintf(buf, sizeof buf, "  const double v%u = F[%d];\n", id, slot[id]);
-                src += buf;
+                out += buf;
             }
             for (size_t i = lo; i < hi;) {
                 size_t j = i + 1;
                 if (use_batches && order_batch[i]) while (j < hi && order_batch[j] == order_batch[i]) j++;
-                if (j - i > 1) em.batch_calls(src, order, i, j);
-                else em.statement(src, order[i]);
+                if (j - i > 1) em.batch_calls(out, order, i, j);
+                else em.statement(out, order[i]);
                 for (size_t m = i; m < j; m++) {
                     uint32_t id = order[m];
-                    if (opt.sync_every && (m - lo) % opt.sync_every == opt.sync_every - 1) src += "  __syncthreads();\n";
+                    if (opt.sync_every && (m - lo) % opt.sync_every == opt.sync_every - 1) out += "  __syncthreads();\n";
                     if (slot[id] >= 0) {
                         std::snprintf(buf, sizeof buf, "  F[%d] = v%u;\n", slot[id], id);
-                        src += buf;
+                        out += buf;
                     }
                 }
                 i = j;
             }
-            src += "}\n";
+            out += "}\n";
+            if (split) modules.push_back(std::move(seg_text));
         }
     }
 
-    const uint32_t block = opt.block ? ((opt.block + 31) / 32) * 32 : 256;
     if (opt.min_blocks_per_sm)
         std::snprintf(buf, sizeof buf, "extern \"C\" __global__ void __launch_bounds__(%u, %u) %s(const MrParams p) {\n",
                       block, opt.min_blocks_per_sm, kJitKernelName);
@@ -369,8 +421,27 @@ std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt,
         info->block = block;
         info->n_col = hoist ? uint32_t(prog.col_values.size()) : 0;
         info->n_row = hoist ? uint32_t(prog.row_values.size()) : 0;
+        info->dynamic_smem_bytes = scratch ? 2 * kScratchRows * block * uint32_t(sizeof(double)) : 0;   // argument rows + result rows
+        info->max_registers = 0;
+        if (opt.min_blocks_per_sm) {
+            uint32_t r = 65536u / (block * opt.min_blocks_per_sm);
+            r &= ~7u;                                   // register allocation granularity
+            info->max_registers = r > 255 ? 255 : r;
+        }
     }
-    return src;
+    modules[0] = std::move(src);
+    return modules;
+}
+}  // namespace
+
+std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt, CodegenInfo* info) {
+    CodegenOptions one = opt;
+    one.separate_segments = false;
+    return generate(prog, one, info)[0];
+}
+
+std::vector<std::string> generate_cuda_modules(const Program& prog, const CodegenOptions& opt, CodegenInfo* info) {
+    return generate(prog, opt, info);
 }
 
 }  // namespace maray

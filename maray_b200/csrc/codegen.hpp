@@ -4,6 +4,7 @@
 // is computed once, all three channels share one kernel, and declarations never collide.
 #pragma once
 #include <string>
+#include <vector>
 
 #include "program.hpp"
 
@@ -36,6 +37,17 @@ struct CodegenOptions {
     // pixel cost more issue slots and exposed latency than the 1 227 mostly one-instruction values
     // they replace.  Kept as MARAY_JIT_HOIST=1 for scenes with expensive x-only/y-only sub-programs.
     bool hoist = false;
+    // Emit every segment function as its own translation unit (generate_cuda_modules): the units are
+    // compiled concurrently with --relocatable-device-code and linked with nvJitLink.  This is what
+    // makes inlining sin/exp/ln affordable in transcendental-heavy programs (inlined bodies cost ~4x
+    // the compile time of out-of-line calls and run ~2x faster: no call ABI, no argument moves).
+    bool separate_segments = false;
+    // Out-of-line sin/exp/ln batches pass arguments and results through per-thread rows of dynamic
+    // shared memory to leaf helpers (device_libm.cuh, "scratch-batched form") instead of through the
+    // call ABI's registers.  false = the register-argument x4/x2 helpers.
+    bool scratch_batches = true;
+    // Independent evaluations per iteration of the batch helpers' loop (2 or 4).
+    uint32_t batch_width = 2;
 };
 
 struct CodegenInfo {
@@ -44,6 +56,10 @@ struct CodegenInfo {
     bool transcendentals_inlined = true;
     uint32_t block = 256;           // threads per block the kernel must be launched with
     uint32_t n_col = 0, n_row = 0;  // doubles per column / per row in the hoisting tables (0 = no prologue)
+    // Register cap implied by __launch_bounds__(block, min_blocks): separately compiled segment
+    // functions do not see the kernel's launch bounds and must be given it as --maxrregcount.
+    uint32_t max_registers = 0;
+    uint32_t dynamic_smem_bytes = 0; // dynamic shared memory the kernel must be launched with (batch scratch)
 };
 
 // Names of the generated kernels (extern "C").
@@ -51,6 +67,10 @@ extern const char* const kJitKernelName;
 constexpr const char* kJitPreXName = "maray_pre_x";
 constexpr const char* kJitPreYName = "maray_pre_y";
 
+// One translation unit (segment functions, if any, as __noinline__ functions of the same unit).
 std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt, CodegenInfo* info);
+// modules[0] holds the kernel (and the scene's constant table); with opt.separate_segments and a
+// segmented program, modules[1..] hold one `mr_segK` device function each.
+std::vector<std::string> generate_cuda_modules(const Program& prog, const CodegenOptions& opt, CodegenInfo* info);
 
 }  // namespace maray

@@ -33,7 +33,30 @@ struct MrD4 { double a, b, c, d; };
 MR_DEFINE_BATCHED(sin)
 MR_DEFINE_BATCHED(exp)
 MR_DEFINE_BATCHED(log)
+#ifdef MR_SCR_STRIDE
+#ifndef MR_DYN_DECL
+#define MR_DYN_DECL extern __shared__ double mr_dyn_f64[];
+#endif
+MR_DYN_DECL
+#define MR_S(k) mr_dyn_f64[(k) * MR_SCR_STRIDE + threadIdx.x]
+#define MR_R(k) MR_S(8 + (k))
+#define MR_DEFINE_SCRATCH_BATCH(fn)                                                                    \
+    MR_PLAIN_FN unsigned int mr_##fn##_batch(const unsigned int n) {                                   \
+        for (unsigned int k = 0; k < n; k++) MR_R(k) = mr_##fn(MR_S(k));                               \
+        return 0u;                                                                                     \
+    }                                                                                                  \
+    MR_PLAIN_FN void mr_##fn##_fix(unsigned int) {}
+MR_DEFINE_SCRATCH_BATCH(sin)
+MR_DEFINE_SCRATCH_BATCH(exp)
+MR_DEFINE_SCRATCH_BATCH(log)
+#endif
 #else
+
+// The out-of-range branch is cold: saying so lets the compiler place its block out of line, so the
+// fast path falls through.  In MBs of straight-line code a TAKEN branch restarts the sequential
+// instruction prefetch, and one per sin/exp/ln is what made inlined transcendental-heavy programs
+// instruction-fetch bound.
+#define MR_UNLIKELY(c) __builtin_expect(!!(c), 0)
 
 #ifdef MR_LIBM_HOST
 #include <math.h>
@@ -151,7 +174,9 @@ MR_FN double mr_sin_fast(double x) {
 // (deep scene 20.0 vs 23.6 ms: nothing but x is live across the libdevice call).
 MR_FN double mr_sin(double x) {
     double r = mr_sin_fast(x);
-    if (!mr_sin_inrange(x)) r = MR_SLOW_SIN(x);
+#ifndef MR_NO_SLOW   /* experiment only: measures what the out-of-range branches cost */
+    if (MR_UNLIKELY(!mr_sin_inrange(x))) r = MR_SLOW_SIN(x);
+#endif
     return r;
 }
 MR_FN double mr_sin_eo(double x) {
@@ -186,7 +211,9 @@ MR_FN double mr_exp_fast(double x) {
 // (deep scene 20.0 vs 23.6 ms: nothing but x is live across the libdevice call).
 MR_FN double mr_exp(double x) {
     double r = mr_exp_fast(x);
-    if (!mr_exp_inrange(x)) r = MR_SLOW_EXP(x);
+#ifndef MR_NO_SLOW   /* experiment only: measures what the out-of-range branches cost */
+    if (MR_UNLIKELY(!mr_exp_inrange(x))) r = MR_SLOW_EXP(x);
+#endif
     return r;
 }
 MR_FN double mr_exp_eo(double x) {
@@ -236,7 +263,9 @@ MR_FN double mr_log_fast(double x) {
 // (deep scene 20.0 vs 23.6 ms: nothing but x is live across the libdevice call).
 MR_FN double mr_log(double x) {
     double r = mr_log_fast(x);
-    if (!mr_log_inrange(x)) r = MR_SLOW_LOG(x);
+#ifndef MR_NO_SLOW   /* experiment only: measures what the out-of-range branches cost */
+    if (MR_UNLIKELY(!mr_log_inrange(x))) r = MR_SLOW_LOG(x);
+#endif
     return r;
 }
 MR_FN double mr_log_eo(double x) {
@@ -262,6 +291,141 @@ struct MrD4 { double a, b, c, d; };
 MR_DEFINE_BATCHED(sin)
 MR_DEFINE_BATCHED(exp)
 MR_DEFINE_BATCHED(log)
+
+// Scratch-batched form (the NVRTC back end's default for transcendental-heavy programs).  Arguments
+// and results travel through a per-thread column of dynamic shared memory, MR_S(k) = row k of this
+// thread, instead of the call ABI's fixed registers: one STS + one LDS per value replaces four moves,
+// and the helper is a LEAF with a two-wide loop -- no nested call, so nothing has to survive one, no
+// callee-saved registers are touched and nothing is spilled (the register-argument x4 helpers above
+// spend 4/5 of their instructions on exactly that).  The loop body is a few hundred bytes and stays
+// in the instruction cache, which is what bounds straight-line code of this size.
+// Out-of-range arguments are left in place and reported in the returned mask; the caller hands the
+// mask to mr_*_fix (libdevice), a call that is practically never executed.
+#ifdef MR_SCR_STRIDE
+extern __shared__ double mr_dyn_f64[];
+#define MR_S(k) mr_dyn_f64[(k) * MR_SCR_STRIDE + threadIdx.x]
+#ifndef MR_BATCH_WIDTH
+#define MR_BATCH_WIDTH 2      /* independent evaluations per loop iteration (2 or 4; the scratch has 8 rows) */
+#endif
+#define MR_W MR_BATCH_WIDTH
+#define MR_EACH _Pragma("unroll") for (int i = 0; i < MR_W; i++)
+// The fast paths again, MR_W evaluations at a time and written STEP-MAJOR: every step is applied to
+// all lanes before the next one, so the lanes' dependent DFMA chains are interleaved in program order.
+// (Left to itself the compiler emits one whole chain after the other -- measured: 47 % of the helpers'
+// cycles were fixed-latency waits on the previous DFMA with 4 warps per scheduler.)  Same operations in
+// the same order per lane as mr_sin_fast / mr_exp_fast / mr_log_fast: bit-identical results.
+__device__ __forceinline__ void mr_sin_fast_w(const double* x, double* out) {
+    double t[MR_W], q[MR_W], r[MR_W], s[MR_W], p[MR_W], k[MR_W][6], sn[MR_W];
+    int qi[MR_W], odd[MR_W];
+    MR_EACH t[i] = MR_FMA(x[i], MR_LK[1], MR_LK[0]);
+    MR_EACH q[i] = t[i] - MR_LK[0];
+    MR_EACH r[i] = MR_FMA(q[i], -MR_LK[2], x[i]);
+    MR_EACH r[i] = MR_FMA(q[i], -MR_LK[3], r[i]);
+    MR_EACH r[i] = MR_FMA(q[i], -MR_LK[4], r[i]);
+    MR_EACH { qi[i] = mr_lo32(t[i]); odd[i] = qi[i] & 1; }
+    MR_EACH {
+        const double* row = MR_SINCOS[odd[i]];
+        MR_LDG2(row + 0, k[i][0], k[i][1]);
+        MR_LDG2(row + 2, k[i][2], k[i][3]);
+        MR_LDG2(row + 4, k[i][4], k[i][5]);
+    }
+    MR_EACH s[i] = r[i] * r[i];
+    MR_EACH p[i] = odd[i] ? MR_LK[27] : MR_LK[26];
+    MR_EACH p[i] = MR_FMA(p[i], s[i], k[i][0]);
+    MR_EACH p[i] = MR_FMA(p[i], s[i], k[i][1]);
+    MR_EACH p[i] = MR_FMA(p[i], s[i], k[i][2]);
+    MR_EACH p[i] = MR_FMA(p[i], s[i], k[i][3]);
+    MR_EACH p[i] = MR_FMA(p[i], s[i], k[i][4]);
+    MR_EACH p[i] = MR_FMA(p[i], s[i], k[i][5]);
+    MR_EACH p[i] = MR_FMA(p[i], s[i], odd[i] ? 1.0 : 0.0);
+    MR_EACH sn[i] = MR_FMA(p[i], r[i], r[i]);
+    MR_EACH {
+        const double v = odd[i] ? p[i] : sn[i];
+        out[i] = mr_hilo((int)((unsigned int)mr_hi32(v) ^ (((unsigned int)qi[i] & 2u) << 30)), mr_lo32(v));
+    }
+}
+__device__ __forceinline__ void mr_exp_fast_w(const double* x, double* out) {
+    double t[MR_W], n[MR_W], r[MR_W], p[MR_W];
+    MR_EACH t[i] = MR_FMA(x[i], MR_LK[5], MR_LK[0]);
+    MR_EACH n[i] = t[i] - MR_LK[0];
+    MR_EACH r[i] = MR_FMA(n[i], -MR_LK[6], x[i]);
+    MR_EACH r[i] = MR_FMA(n[i], -MR_LK[7], r[i]);
+    MR_EACH p[i] = MR_LK[8];
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[9]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[10]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[11]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[12]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[13]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[14]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[15]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[16]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[17]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], MR_LK[18]);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], 1.0);
+    MR_EACH p[i] = MR_FMA(p[i], r[i], 1.0);
+    MR_EACH out[i] = mr_hilo((int)((unsigned int)mr_hi32(p[i]) + ((unsigned int)mr_lo32(t[i]) << 20)), mr_lo32(p[i]));
+}
+__device__ __forceinline__ void mr_log_fast_w(const double* x, double* out) {
+    double m[MR_W], a[MR_W], b[MR_W], y[MR_W], er[MR_W], u[MR_W], d[MR_W], rem[MR_W], u_lo[MR_W], w[MR_W], Q[MR_W];
+    double t3[MR_W], ed[MR_W], h[MR_W], c[MR_W], lo[MR_W];
+    MR_EACH {
+        const int hx = mr_hi32(x[i]);
+        int e = (hx >> 20) - 1023;
+        int mh = (hx & 0x000fffff) | 0x3ff00000;
+        if (mh >= 0x3ff6a09f) { mh -= 0x00100000; e += 1; }
+        m[i] = mr_hilo(mh, mr_lo32(x[i]));
+        ed[i] = (double)e;
+    }
+    MR_EACH a[i] = m[i] - 1.0;
+    MR_EACH b[i] = m[i] + 1.0;
+    MR_EACH y[i] = mr_rcp_approx(b[i]);
+    MR_EACH er[i] = MR_FMA(-b[i], y[i], 1.0);
+    MR_EACH y[i] = MR_FMA(y[i], er[i], y[i]);
+    MR_EACH er[i] = MR_FMA(-b[i], y[i], 1.0);
+    MR_EACH y[i] = MR_FMA(y[i], er[i], y[i]);
+    MR_EACH { const double qq = a[i] * y[i]; u[i] = qq + qq; }
+    MR_EACH d[i] = a[i] - u[i];
+    MR_EACH rem[i] = MR_FMA(a[i], -u[i], d[i] + d[i]);
+    MR_EACH u_lo[i] = y[i] * rem[i];
+    MR_EACH w[i] = u[i] * u[i];
+    MR_EACH Q[i] = MR_LK[19];
+    MR_EACH Q[i] = MR_FMA(Q[i], w[i], MR_LK[20]);
+    MR_EACH Q[i] = MR_FMA(Q[i], w[i], MR_LK[21]);
+    MR_EACH Q[i] = MR_FMA(Q[i], w[i], MR_LK[22]);
+    MR_EACH Q[i] = MR_FMA(Q[i], w[i], MR_LK[23]);
+    MR_EACH Q[i] = MR_FMA(Q[i], w[i], MR_LK[24]);
+    MR_EACH Q[i] = MR_FMA(Q[i], w[i], MR_LK[25]);
+    MR_EACH t3[i] = MR_FMA(u[i] * w[i], Q[i], u_lo[i]);
+    MR_EACH h[i] = MR_FMA(ed[i], MR_LK[6], u[i]);
+    MR_EACH c[i] = MR_FMA(ed[i], MR_LK[6], -h[i]) + u[i];
+    MR_EACH lo[i] = MR_FMA(ed[i], MR_LK[7], t3[i]) + c[i];
+    MR_EACH out[i] = h[i] + lo[i];
+}
+// Rows 0..7 of the scratch hold the arguments and are left intact; results go to rows 8..15
+// (MR_R(k)).  The helper returns one flag, "some argument was outside the fast range", and mr_*_fix
+// then recomputes exactly those rows with libdevice: no per-lane mask, no selects on the stores.
+#define MR_R(k) MR_S(8 + (k))
+#define MR_DEFINE_SCRATCH_BATCH(fn, SLOW)                                                              \
+    static __device__ __noinline__ unsigned int mr_##fn##_batch(const unsigned int n) {                \
+        bool all_ok = true;                                                                            \
+        double* s = mr_dyn_f64 + threadIdx.x;                                                          \
+        for (unsigned int k = 0; k < n; k += MR_W, s += MR_W * MR_SCR_STRIDE) {                        \
+            double x[MR_W], r[MR_W];                                                                   \
+            MR_EACH x[i] = s[i * MR_SCR_STRIDE];   /* rows past n: stale but in bounds, results unused */ \
+            mr_##fn##_fast_w(x, r);                                                                    \
+            MR_EACH s[(8 + i) * MR_SCR_STRIDE] = r[i];                                                 \
+            MR_EACH all_ok &= mr_##fn##_inrange(x[i]) || (i != 0 && k + i >= n);                       \
+        }                                                                                              \
+        return all_ok ? 0u : 1u;                                                                       \
+    }                                                                                                  \
+    static __device__ __noinline__ void mr_##fn##_fix(const unsigned int n) {                          \
+        for (unsigned int k = 0; k < n; k++)                                                           \
+            if (!mr_##fn##_inrange(MR_S(k))) MR_R(k) = SLOW(MR_S(k));                                  \
+    }
+MR_DEFINE_SCRATCH_BATCH(sin, MR_SLOW_SIN)
+MR_DEFINE_SCRATCH_BATCH(exp, MR_SLOW_EXP)
+MR_DEFINE_SCRATCH_BATCH(log, MR_SLOW_LOG)
+#endif  // MR_SCR_STRIDE
 #endif
 
 #endif  // MR_LIBM_PLAIN

@@ -83,10 +83,15 @@ bool read_png_rgb8(const std::string& path, uint32_t* w_out, uint32_t* h_out, st
     }
     if (!w || !h || ctype < 0) return fail("missing IHDR");
     if (interlace) return fail("interlaced PNG is not supported");
-    if (depth != 8 && depth != 16) return fail("only bit depths 8 and 16 are supported");
     int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-    if (!channels || (ctype == 3 && depth != 8)) return fail("unsupported colour type");
-    const size_t bpp = size_t(channels) * (depth / 8), stride = size_t(w) * bpp;
+    if (!channels) return fail("unsupported colour type");
+    // PNG allows 1/2/4-bit samples for greyscale and palette images only, 16-bit for everything but palette
+    const bool sub_byte = depth == 1 || depth == 2 || depth == 4;
+    if (!(depth == 8 || (depth == 16 && ctype != 3) || (sub_byte && (ctype == 0 || ctype == 3))))
+        return fail("unsupported bit depth for this colour type");
+    // bytes per complete pixel as the filters see it (1 for sub-byte samples), bytes per row
+    const size_t bpp = sub_byte ? 1 : size_t(channels) * (depth / 8);
+    const size_t stride = sub_byte ? (size_t(w) * depth + 7) / 8 : size_t(w) * bpp;
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf rawlen = uLongf(raw.size());
     if (uncompress(raw.data(), &rawlen, idat.data(), uLong(idat.size())) != Z_OK || rawlen != raw.size()) return fail("corrupt image data");
@@ -110,7 +115,15 @@ bool read_png_rgb8(const std::string& path, uint32_t* w_out, uint32_t* h_out, st
         uint8_t* dst = &(*rgb)[size_t(y) * w * 3];
         const size_t sample = depth / 8;   // 16-bit: big-endian, keep the high byte
         for (uint32_t xx = 0; xx < w; xx++) {
+            uint8_t packed;
             const uint8_t* px = &cur[xx * bpp];
+            if (sub_byte) {
+                // samples are packed most significant first; greyscale is scaled to 0..255 (v * 255 / max)
+                const unsigned bit = unsigned(xx) * unsigned(depth);
+                const unsigned v = (cur[bit >> 3] >> (8 - depth - (bit & 7))) & ((1u << depth) - 1u);
+                packed = ctype == 0 ? uint8_t(v * 255u / ((1u << depth) - 1u)) : uint8_t(v);
+                px = &packed;
+            }
             switch (ctype) {
             case 0: case 4: dst[3 * xx] = dst[3 * xx + 1] = dst[3 * xx + 2] = px[0]; break;
             case 2: case 6: dst[3 * xx] = px[0]; dst[3 * xx + 1] = px[sample]; dst[3 * xx + 2] = px[2 * sample]; break;

@@ -61,3 +61,44 @@ def test_cli_renders_textured_scene_like_the_oracle(tmp_path, backend):
     got = np.array(Image.open(out).convert("RGB"))
     want = OracleScene(scene_bytes, arrays).render()
     assert np.array_equal(got, want)
+
+
+def test_png_codec_reads_what_pillow_writes(tmp_path):
+    """The CLI's built-in PNG codec (csrc/png.cpp) against Pillow, on the CPU: RGB, RGBA, 8/4/2/1-bit
+    palette, 8/4/2/1-bit and 16-bit grey must decode to what `convert("RGB")` gives (16-bit: the high
+    byte), and what the writer writes must read back unchanged."""
+    csrc = os.path.join(ROOT, "maray_b200", "csrc")
+    exe = str(tmp_path / "pngtool")
+    (tmp_path / "pngtool.cpp").write_text(r'''
+#include "png.hpp"
+#include <cstdio>
+int main(int argc, char** argv) {
+    std::vector<uint8_t> rgb; uint32_t w = 0, h = 0; std::string err;
+    if (!maray::read_png_rgb8(argv[1], &w, &h, &rgb, &err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    if (argc > 2 && !maray::write_png_rgb8(argv[2], w, h, rgb.data(), &err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    std::fwrite(rgb.data(), 1, rgb.size(), stdout);
+    return 0;
+}''')
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", csrc, "-o", exe, str(tmp_path / "pngtool.cpp"),
+                           os.path.join(csrc, "png.cpp"), "-lz"])
+    rgb = scenes.synthetic_textures(1, 37)[0][:29]          # odd sizes: rows do not end on byte boundaries
+    grey = rgb[:, :, 0]
+    cases = {"rgb": Image.fromarray(rgb), "rgba": Image.fromarray(np.dstack([rgb, grey]), "RGBA"),
+             "grey8": Image.fromarray(grey), "grey16": Image.fromarray((grey.astype(np.uint16) << 8) | 0x5A),
+             "bilevel": Image.fromarray(grey > 100)}
+    for colours in (256, 16, 4, 2):
+        cases[f"pal{colours}"] = Image.fromarray(rgb).quantize(colours)
+    for name, img in cases.items():
+        path = str(tmp_path / f"{name}.png")
+        bits = {"pal16": 4, "pal4": 2, "pal2": 1}.get(name)
+        img.save(path, **({"bits": bits} if bits else {}))
+        back = str(tmp_path / f"{name}_back.png")
+        r = subprocess.run([exe, path, back], capture_output=True)
+        assert r.returncode == 0, (name, r.stderr)
+        got = np.frombuffer(r.stdout, np.uint8).reshape(29, 37, 3)
+        if name == "grey16":
+            want = np.repeat(grey[:, :, None], 3, axis=2)
+        else:
+            want = np.array(img.convert("RGB"))
+        assert np.array_equal(got, want), name
+        assert np.array_equal(np.array(Image.open(back).convert("RGB")), want), name

@@ -174,6 +174,66 @@ def test_deep_transcendental_scene_within_tolerance(backend):
     assert np.nanmax(rel) < 1e-12
 
 
+def _heavy_scene_with_out_of_range_arguments(w, h):
+    """>= 2048 sin/exp/ln values (so the NVRTC back end batches them through out-of-line helpers) plus
+    arguments outside every fast range: sin of ~1e9 and of inf (NaN), exp beyond 709 (inf) and below
+    -745 (0), ln of a negative (NaN), of 0 (-inf) and of a subnormal."""
+    _size, color, _ = E.from_bytes(scenes.deep(w, h, n_values=9000, seed=3))
+    x, y = E.x(), E.y()
+    inf = E.recip(E.nat(0))
+    tiny = E.exp(E.neg(E.nat(740)))                                   # subnormal constant, folded on the host
+    odd = [
+        E.sin(E.mul(E.add(x, E.nat(3)), E.nat(123456789))),            # huge: Payne-Hanek territory
+        E.sin(E.mul(inf, E.add(x, E.nat(1)))),                          # sin(inf) = NaN
+        E.exp(E.mul(E.add(y, E.nat(1)), E.nat(400))),                   # overflow to inf
+        E.exp(E.neg(E.mul(E.add(y, E.nat(2)), E.nat(400)))),            # underflow to 0
+        E.ln(E.add(x, E.neg(E.nat(5)))),                                # negative -> NaN, 0 -> -inf
+        E.ln(E.mul(tiny, E.add(x, E.nat(1)))),                          # subnormal argument
+    ]
+    # f64::max/min ignore NaN (reference src/lib.rs:652-655), so every channel stays defined
+    extra = [E.mul(E.max(E.nat(0), E.min(E.nat(1), E.mul(t, t))), E.nat(40)) for t in odd]
+    def inner(c):
+        return c.a if c.tag == E.LET else c
+    assert all(c.tag == E.LET for c in color)
+    out = []
+    for i, c in enumerate(color):
+        body = E.add(E.add(c.a, extra[2 * i]), extra[2 * i + 1])
+        out.append(E.let_(c.vars, body))
+    return E.to_bytes([w, h], out)
+
+
+@pytest.mark.parametrize("form", ["scratch", "registers", "separate_units"])
+def test_batched_transcendentals_and_their_repair_path(monkeypatch, form):
+    """The out-of-line sin/exp/ln forms of the NVRTC back end on a program above the batching threshold,
+    with arguments that must take the libdevice repair path.  All forms run the same device routines,
+    so their f64 planes must be bit-identical to each other; against the oracle the usual tolerance."""
+    w, h = 96, 64
+    scene = _heavy_scene_with_out_of_range_arguments(w, h)
+    want_rgb, want = OracleScene(scene).render_window(0, w, 0, h, want_f64=True)
+    if form == "registers":
+        monkeypatch.setenv("MARAY_JIT_SCRATCH", "0")
+    if form == "separate_units":
+        monkeypatch.setenv("MARAY_JIT_PARALLEL", "1")
+        monkeypatch.setenv("MARAY_JIT_SEGMENT_VALUES", "4096")
+    with _renderer(scene, "nvrtc") as r:
+        st = r.stats()
+        planes, rgb = r.render_window_f64(w, h, 0, w, 0, h)
+        frame = r.render(w, h)
+    if form == "separate_units":
+        assert st["jit_units"] > 1 and st["link_ms"] > 0
+    assert np.array_equal(frame, rgb)
+    monkeypatch.delenv("MARAY_JIT_SCRATCH", raising=False)
+    monkeypatch.delenv("MARAY_JIT_PARALLEL", raising=False)
+    monkeypatch.delenv("MARAY_JIT_SEGMENT_VALUES", raising=False)
+    # yardstick: the interpreter kernel, whose handlers inline the scalar routines
+    with _renderer(scene, "interp") as r:
+        ref_planes, ref_rgb = r.render_window_f64(w, h, 0, w, 0, h)
+    assert bits_equal(planes, ref_planes).all(), "batched and inlined sin/exp/ln disagree"
+    assert np.array_equal(rgb, ref_rgb)
+    n_diff, n_bad = _attribute_mismatches(scene, rgb, want_rgb)
+    assert n_bad == 0 and n_diff <= max(1, w * h // 10000)
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_nan_inf_zero_semantics_on_device(backend):
     x = E.x()

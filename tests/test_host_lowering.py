@@ -121,8 +121,17 @@ def test_hoisting_option_is_value_preserving(monkeypatch, chess_bytes):
             assert np.array_equal(rgb, want_rgb.reshape(w, 3))
 
 
-def test_transcendental_batching_keeps_values(monkeypatch):
-    """Programs with >= 2048 sin/exp/ln values get their schedule batched and call x4/x2 helpers."""
+@pytest.mark.parametrize("form", ["scratch", "registers", "separate_units"])
+def test_transcendental_batching_keeps_values(monkeypatch, form):
+    """Programs with >= 2048 sin/exp/ln values get their schedule batched and call out-of-line helpers:
+    through the per-thread shared-memory scratch (default), through register arguments (x4/x2), or --
+    MARAY_JIT_PARALLEL=1 -- with every segment function in its own translation unit (linked with
+    nvJitLink; the text checked here is the same statements as one unit)."""
+    if form == "registers":
+        monkeypatch.setenv("MARAY_JIT_SCRATCH", "0")
+    if form == "separate_units":
+        monkeypatch.setenv("MARAY_JIT_PARALLEL", "1")
+        monkeypatch.setenv("MARAY_JIT_SEGMENT_VALUES", "4096")
     scene = scenes.deep(48, 32, n_values=9000, seed=3)
     with CudaRenderer(gpus=0) as r:
         r.load(scene)
@@ -131,9 +140,35 @@ def test_transcendental_batching_keeps_values(monkeypatch):
         r.compile("interp")
         code, consts = r.bytecode()
     assert st["n_sin"] + st["n_exp"] + st["n_ln"] >= 2048
-    assert "_x4(" in src[src.index('extern "C" __global__'):]
+    body = src[src.index("mr_seg0") if "mr_seg0" in src else src.index('extern "C" __global__'):]
+    assert ("_x4(" in body) if form == "registers" else ("_batch(" in body and "MR_R(" in body)
+    if form == "separate_units":
+        assert st["jit_units"] == st["jit_segments"] + 1 and st["jit_segments"] >= 2 and st["jit_compile_threads"] >= 1
+        assert st["link_ms"] > 0 and st["jit_cubin_bytes"] > 1000
+    else:
+        assert st["jit_units"] == 1 and st["link_ms"] == 0
     want_rgb, want = _oracle_window(scene, [], 0, 48, 7, 8)
     rgb, planes = host_jit_run(src, 48, 7 * 48, 48)
     assert bits_equal(planes, want.reshape(3, 48)).all() and np.array_equal(rgb, want_rgb.reshape(48, 3))
     bc = bytecode_run(code, consts, np.arange(48), np.full(48, 7))
     assert bits_equal(bc, want.reshape(3, 48)).all()
+
+
+def test_cubin_cache_round_trip(monkeypatch, tmp_path):
+    """MARAY_JIT_CACHE: the second compile of the same scene with the same options loads the cubin
+    from the directory (no NVRTC run); a different option misses."""
+    monkeypatch.setenv("MARAY_JIT_CACHE", str(tmp_path))
+    scene = scenes.sdf(64, 48, 6, seed=4)
+    stats = []
+    for _ in range(2):
+        with CudaRenderer(gpus=0) as r:
+            r.load(scene)
+            stats.append(r.compile("nvrtc"))
+    assert stats[0]["jit_cache_hit"] == 0 and stats[1]["jit_cache_hit"] == 1
+    assert stats[0]["jit_cubin_bytes"] == stats[1]["jit_cubin_bytes"] and stats[1]["jit_registers"] == stats[0]["jit_registers"]
+    assert len(list(tmp_path.glob("*.mrcubin"))) == 1
+    monkeypatch.setenv("MARAY_JIT_MIN_BLOCKS", "1")
+    with CudaRenderer(gpus=0) as r:
+        r.load(scene)
+        assert r.compile("nvrtc")["jit_cache_hit"] == 0
+    assert len(list(tmp_path.glob("*.mrcubin"))) == 2
