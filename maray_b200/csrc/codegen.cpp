@@ -42,6 +42,25 @@ struct Emitter {
     const std::vector<uint8_t>* load_kind = nullptr;
     const std::vector<uint32_t>* table_index = nullptr;
     bool scratch_batches = false;
+    // Values that are exactly +0.0 or 1.0 at every pixel (see find_booleans): kind 1 = boolean,
+    // kind 2 = the NOT pattern `1 + -(b)`.  Emitted as `bool` logic plus a double shadow.
+    const std::vector<uint8_t>* boolean = nullptr;
+
+    bool is_bool(uint32_t id) const { return boolean && (*boolean)[id]; }
+    void bool_operand(std::string& s, uint32_t id) const {
+        const Node& n = P.nodes[id];
+        if (n.op == OP_CONST) { s += (n.k != 0.0) ? "true" : "false"; return; }
+        char buf[16];
+        std::snprintf(buf, sizeof buf, "b%u", id);
+        s += buf;
+    }
+    // `const bool bN = vN != 0.0;` after a boolean value arrived as a double (frame import, table load)
+    void bool_from_double(std::string& s, uint32_t id) const {
+        if (!is_bool(id)) return;
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "  const bool b%u = v%u != 0.0;\n", id, id);
+        s += buf;
+    }
 
     void operand(std::string& s, uint32_t id) const {
         const Node& n = P.nodes[id];
@@ -110,6 +129,26 @@ struct Emitter {
             if ((*load_kind)[id] == 1) std::snprintf(buf, sizeof buf, "  const double v%u = __ldg(CV + %uu * CW);\n", id, (*table_index)[id]);
             else std::snprintf(buf, sizeof buf, "  const double v%u = __ldg(RV + %uu * RW);\n", id, (*table_index)[id]);
             s += buf;
+            bool_from_double(s, id);
+            return;
+        }
+        if (is_bool(id)) {
+            // 0/1-valued: compares and bit logic instead of FP64 multiplies, min/max and selects.  The
+            // double shadow is what every non-boolean consumer reads; unused shadows are dead code.
+            std::snprintf(buf, sizeof buf, "  const bool b%u = ", id);
+            s += buf;
+            switch (n.op) {
+            case OP_STEP: s += "("; operand(s, n.a); s += " >= 0.0)"; break;          // NaN -> false, -0.0 -> true
+            case OP_ADD: {                                                           // 1 + -(b)  ==  !b
+                const uint32_t neg = P.nodes[n.a].op == OP_NEG ? n.a : n.b;
+                s += "!"; bool_operand(s, P.nodes[neg].a);
+            } break;
+            case OP_MUL: case OP_MIN: s += "("; bool_operand(s, n.a); s += " && "; bool_operand(s, n.b); s += ")"; break;
+            case OP_MAX: s += "("; bool_operand(s, n.a); s += " || "; bool_operand(s, n.b); s += ")"; break;
+            default: s += "false"; break;
+            }
+            std::snprintf(buf, sizeof buf, ";\n  const double v%u = b%u ? 1.0 : 0.0;\n", id, id);
+            s += buf;
             return;
         }
         std::snprintf(buf, sizeof buf, "  const double v%u = ", id);
@@ -146,6 +185,34 @@ struct Emitter {
 }  // namespace
 
 namespace {
+// Values that are exactly +0.0 or 1.0 whatever the pixel: step(..), the constants 0 and 1, products /
+// min / max of two such values (AND, AND, OR), and `1 + -(b)` (NOT).  All of these identities are exact
+// in IEEE arithmetic (0*1 = +0, 1 + -1 = +0 under round-to-nearest, min/max of {+0, 1} never see a NaN
+// or a -0), so evaluating them as boolean logic changes no bit of any channel.  Scenes built from
+// Maray's set algebra (range, set_and/or/xor/inv, inside_triangle; reference src/lib.rs:869-913,
+// 1094-1097) are mostly made of them: chess has 1 482 steps, 768 min, 256 max.
+std::vector<uint8_t> find_booleans(const Program& prog) {
+    const size_t n = prog.nodes.size();
+    std::vector<uint8_t> kind(n, 0);
+    auto is_one = [&](uint32_t v) { return prog.nodes[v].op == OP_CONST && prog.nodes[v].k == 1.0; };
+    auto neg_of_bool = [&](uint32_t v) { return prog.nodes[v].op == OP_NEG && kind[prog.nodes[v].a]; };
+    for (size_t i = 0; i < n; i++) {
+        const Node& nd = prog.nodes[i];
+        switch (nd.op) {
+        case OP_CONST: {
+            uint64_t bits;
+            std::memcpy(&bits, &nd.k, 8);
+            kind[i] = (bits == 0 || nd.k == 1.0) ? 1 : 0;          // +0.0 only: -0.0 is not a boolean
+        } break;
+        case OP_STEP: kind[i] = 1; break;
+        case OP_MUL: case OP_MIN: case OP_MAX: kind[i] = (kind[nd.a] && kind[nd.b]) ? 1 : 0; break;
+        case OP_ADD: kind[i] = ((is_one(nd.a) && neg_of_bool(nd.b)) || (neg_of_bool(nd.a) && is_one(nd.b))) ? 2 : 0; break;
+        default: break;
+        }
+    }
+    return kind;
+}
+
 // Common generator.  modules[0] always holds the kernel; with opt.separate_segments (and a segmented
 // program) every segment function is its own translation unit in modules[1..].
 std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt, CodegenInfo* info) {
@@ -200,6 +267,8 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         }
     }
     Emitter em{prog, n_trans < opt.inline_transcendentals_below, opt.constants_in_bank ? &bank_index : nullptr};
+    const std::vector<uint8_t> booleans = opt.boolean_logic ? find_booleans(prog) : std::vector<uint8_t>();
+    if (opt.boolean_logic) em.boolean = &booleans;
     Emitter em_pre = em;                       // prologue kernels compute hoisted values, never load them
     if (hoist) { em.load_kind = &load_kind; em.table_index = &table_index; }
 
@@ -320,6 +389,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
             for (uint32_t id : imports) {
                 std::snprintf(buf, sizeof buf, "  const double v%u = F[%d];\n", id, slot[id]);
                 out += buf;
+                em.bool_from_double(out, id);
             }
             for (size_t i = lo; i < hi;) {
                 size_t j = i + 1;

@@ -17,8 +17,25 @@ __device__ __forceinline__ double mr_step(double v) { return (v >= 0.0) ? 1.0 : 
 // tie (incl. +0/-0) the FIRST operand is returned.  reference src/lib.rs:655-658; DESIGN.md
 // "Semantics".  (CUDA's fmax/fmin would return +0 for max(-0,+0) regardless of order.)
 // Written as one select on (b > a || isnan(a)): 2 DSETP + 2 FSEL in SASS.
-__device__ __forceinline__ double mr_max(double a, double b) { return ((b > a) || (a != a)) ? b : a; }
-__device__ __forceinline__ double mr_min(double a, double b) { return ((b < a) || (a != a)) ? b : a; }
+//
+// The select itself is inline PTX on purpose.  Written as `cond ? b : a`, NVVM recognises the pattern
+// (whenever `a` is a literal, so `a != a` folds away) and emits PTX min.f64 / max.f64, and ptxas then
+// re-associates a max(0, min(1, t)) pair into min(1, max(0, t)) -- equal for numbers, but for t = NaN
+// the first form is 1 (NaN ignored, then max(0,1)) and the second is 0.  Measured on sm_100a with
+// CUDA 12.9: `max(0, min(1, ln(x-5)^2))` rendered 0 instead of 1 wherever the logarithm was NaN
+// (tests/test_gpu_parity.py::test_batched_transcendentals_and_their_repair_path).  An opaque selp keeps
+// the compare-and-select exactly as written; the cost is the same 2 DSETP + 2 FSEL (1 + 2 for a literal).
+#ifdef MR_HOST_TEXT   /* tests/helpers.py compiles the generated text as plain C++ */
+static inline double mr_pick(bool take_b, double a, double b) { return take_b ? b : a; }
+#else
+__device__ __forceinline__ double mr_pick(bool take_b, double a, double b) {
+    double r;
+    asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.f64 %0, %2, %1, p; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)take_b));
+    return r;
+}
+#endif
+__device__ __forceinline__ double mr_max(double a, double b) { return mr_pick((b > a) || (a != a), a, b); }
+__device__ __forceinline__ double mr_min(double a, double b) { return mr_pick((b < a) || (a != a), a, b); }
 
 // Recip(a) = 1.0 / a, IEEE round-to-nearest.  reference src/lib.rs:642
 __device__ __forceinline__ double mr_recip(double v) { return __drcp_rn(v); }

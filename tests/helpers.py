@@ -33,6 +33,7 @@ HOST_SHIM = r"""
 #define __launch_bounds__(...)
 #define MR_LIBM_PLAIN 1          /* the host check uses the host libm, like the oracle */
 #define MR_PLAIN_FN static inline
+#define MR_HOST_TEXT 1
 #define MR_DYN_DECL static double mr_dyn_f64[32 * 256];   /* the scratch rows of the batched sin/exp/ln calls */
 struct uint3_ { unsigned int x, y, z; };
 static uint3_ threadIdx, blockIdx, blockDim;

@@ -255,6 +255,29 @@ def test_nan_inf_zero_semantics_on_device(backend):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+def test_clamp_of_nan_with_literal_bounds(backend):
+    """max(0, min(1, t)) with literal bounds and t = NaN must be 1 (f64::min ignores the NaN, reference
+    src/lib.rs:655-658); the compiler's own min/max pattern turns the pair into min(1, max(0, t)) = 0
+    (device_sem.cuh, mr_pick).  Also the mirrored clamp, and bounds on the other side."""
+    x = E.x()
+    inf = E.recip(E.nat(0))
+    t_nan = E.mul(E.mul(inf, E.nat(0)), E.add(x, E.nat(1)))           # NaN at every pixel, not foldable
+    t_mixed = E.ln(E.add(x, E.neg(E.nat(3))))                         # NaN for x < 3, -inf at 3, numbers after
+    def clamp(t): return E.max(E.nat(0), E.min(E.nat(1), t))
+    def clamp_rev(t): return E.min(E.nat(1), E.max(E.nat(0), t))
+    color = [E.mul(clamp(t_nan), E.nat(200)),
+             E.mul(clamp(E.mul(t_mixed, t_mixed)), E.nat(200)),
+             E.mul(E.add(clamp_rev(t_mixed), E.max(E.min(t_mixed, E.nat(1)), E.nat(0))), E.nat(100))]
+    scene = E.to_bytes([8, 1], color)
+    want_rgb, want = OracleScene(scene).render_window(0, 8, 0, 1, want_f64=True)
+    assert want[0, 0, 0] == 200.0 and want[1, 0, 0] == 200.0          # the NaN is ignored: min gives the bound 1
+    with _renderer(scene, backend) as r:
+        planes, rgb = r.render_window_f64(8, 1, 0, 8, 0, 1)
+    assert np.array_equal(rgb, want_rgb)
+    assert (np.abs(planes - want) <= 1e-13 * np.abs(want)).all()      # ln differs from glibc in the last bits only
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_ragged_sizes_bands_and_windows(backend):
     """Odd widths (unaligned row starts), a 1x1 image, bands that do not divide the height."""
     scene = scenes.sdf(333, 77, 5, seed=8)
