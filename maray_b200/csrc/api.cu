@@ -735,6 +735,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         if (const char* e = std::getenv("MARAY_JIT_HOIST")) copt.hoist = std::strtoul(e, nullptr, 10) != 0;
         if (const char* e = std::getenv("MARAY_JIT_BOOLEAN")) copt.boolean_logic = std::strtoul(e, nullptr, 10) != 0;
         if (const char* e = std::getenv("MARAY_JIT_SCRATCH")) copt.scratch_batches = std::strtoul(e, nullptr, 10) != 0;
+        if (const char* e = std::getenv("MARAY_JIT_PRIVATE_HELPERS")) copt.private_batch_helpers = std::strtoul(e, nullptr, 10) != 0;
         if (const char* e = std::getenv("MARAY_JIT_BATCH_WIDTH")) copt.batch_width = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_BLOCK")) copt.block = uint32_t(std::strtoul(e, nullptr, 10));
         if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10));

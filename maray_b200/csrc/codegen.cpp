@@ -42,6 +42,7 @@ struct Emitter {
     const std::vector<uint8_t>* load_kind = nullptr;
     const std::vector<uint32_t>* table_index = nullptr;
     bool scratch_batches = false;
+    std::string helper_suffix;      // which instance of the batch helpers this function calls ("" or "_sK")
     // Values that are exactly +0.0 or 1.0 at every pixel (see find_booleans): kind 1 = boolean,
     // kind 2 = the NOT pattern `1 + -(b)`.  Emitted as `bool` logic plus a double shadow.
     const std::vector<uint8_t>* boolean = nullptr;
@@ -95,7 +96,8 @@ struct Emitter {
                     std::snprintf(buf, sizeof buf, "  MR_S(%zu) = ", m);
                     s += buf; operand(s, P.nodes[order[i + m]].a); s += ";\n";
                 }
-                std::snprintf(buf, sizeof buf, "  if (mr_%s_batch(%zuu)) mr_%s_fix(%zuu);\n", fn, k, fn, k);
+                std::snprintf(buf, sizeof buf, "  if (mr_%s_batch%s(%zuu)) mr_%s_fix%s(%zuu);\n", fn, helper_suffix.c_str(), k, fn,
+                              helper_suffix.c_str(), k);
                 s += buf;
                 for (size_t m = 0; m < k; m++) {
                     std::snprintf(buf, sizeof buf, "  const double v%u = MR_R(%zu);\n", order[i + m], m);
@@ -282,7 +284,10 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
     const bool scratch = use_batches && opt.scratch_batches;
     em.scratch_batches = scratch;
     std::string prelude = "// generated by maray_b200 (NVRTC back end); compiled with --fmad=false\n";
+    // one private instance of the batch helpers per segment function of a single-unit program
+    const bool private_helpers = scratch && segmented && !split && opt.private_batch_helpers;
     if (scratch) {
+        if (private_helpers) prelude += "#define MR_NO_DEFAULT_BATCH_HELPERS 1\n";
         prelude += "#define MR_SCR_STRIDE " + std::to_string(block) + "\n";
         prelude += "#define MR_BATCH_WIDTH " + std::to_string(opt.batch_width == 4 ? 4 : 2) + "\n";
     }
@@ -365,6 +370,12 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
                 seg_text += bank_extern;
                 std::snprintf(buf, sizeof buf, "__device__ void mr_seg%u", s);
             } else {
+                if (private_helpers) {
+                    std::snprintf(buf, sizeof buf, "MR_BATCH_HELPERS(_s%u)\n", s);
+                    src += buf;
+                    std::snprintf(buf, sizeof buf, "_s%u", s);
+                    em.helper_suffix = buf;
+                }
                 std::snprintf(buf, sizeof buf, "__device__ __noinline__ void mr_seg%u", s);
             }
             out += buf; out += kSegArgs; out += " {\n";

@@ -48,6 +48,8 @@ struct CodegenOptions {
     bool scratch_batches = true;
     // Independent evaluations per iteration of the batch helpers' loop (2 or 4).
     uint32_t batch_width = 2;
+    // In a segmented single-unit program every segment function gets its own copy of the batch helpers.
+    bool private_batch_helpers = true;
     // Evaluate values that are exactly 0.0 or 1.0 at every pixel (step, products/min/max of such
     // values, 1 - b) as boolean logic instead of FP64 arithmetic.  Exact: no channel bit changes.
     bool boolean_logic = true;

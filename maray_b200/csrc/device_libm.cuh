@@ -40,15 +40,16 @@ MR_DEFINE_BATCHED(log)
 MR_DYN_DECL
 #define MR_S(k) mr_dyn_f64[(k) * MR_SCR_STRIDE + threadIdx.x]
 #define MR_R(k) MR_S(8 + (k))
-#define MR_DEFINE_SCRATCH_BATCH(fn)                                                                    \
-    MR_PLAIN_FN unsigned int mr_##fn##_batch(const unsigned int n) {                                   \
+#define MR_DEFINE_SCRATCH_BATCH_S(fn, SUF)                                                                  \
+    MR_PLAIN_FN unsigned int mr_##fn##_batch##SUF(const unsigned int n) {                                   \
         for (unsigned int k = 0; k < n; k++) MR_R(k) = mr_##fn(MR_S(k));                               \
         return 0u;                                                                                     \
     }                                                                                                  \
-    MR_PLAIN_FN void mr_##fn##_fix(unsigned int) {}
-MR_DEFINE_SCRATCH_BATCH(sin)
-MR_DEFINE_SCRATCH_BATCH(exp)
-MR_DEFINE_SCRATCH_BATCH(log)
+    MR_PLAIN_FN void mr_##fn##_fix##SUF(unsigned int) {}
+#define MR_BATCH_HELPERS(SUF) MR_DEFINE_SCRATCH_BATCH_S(sin, SUF) MR_DEFINE_SCRATCH_BATCH_S(exp, SUF) MR_DEFINE_SCRATCH_BATCH_S(log, SUF)
+#ifndef MR_NO_DEFAULT_BATCH_HELPERS
+MR_BATCH_HELPERS()
+#endif
 #endif
 #else
 
@@ -405,8 +406,8 @@ __device__ __forceinline__ void mr_log_fast_w(const double* x, double* out) {
 // (MR_R(k)).  The helper returns one flag, "some argument was outside the fast range", and mr_*_fix
 // then recomputes exactly those rows with libdevice: no per-lane mask, no selects on the stores.
 #define MR_R(k) MR_S(8 + (k))
-#define MR_DEFINE_SCRATCH_BATCH(fn, SLOW)                                                              \
-    static __device__ __noinline__ unsigned int mr_##fn##_batch(const unsigned int n) {                \
+#define MR_DEFINE_SCRATCH_BATCH_S(fn, SLOW, SUF)                                                              \
+    static __device__ __noinline__ unsigned int mr_##fn##_batch##SUF(const unsigned int n) {                \
         bool all_ok = true;                                                                            \
         double* s = mr_dyn_f64 + threadIdx.x;                                                          \
         for (unsigned int k = 0; k < n; k += MR_W, s += MR_W * MR_SCR_STRIDE) {                        \
@@ -418,13 +419,20 @@ __device__ __forceinline__ void mr_log_fast_w(const double* x, double* out) {
         }                                                                                              \
         return all_ok ? 0u : 1u;                                                                       \
     }                                                                                                  \
-    static __device__ __noinline__ void mr_##fn##_fix(const unsigned int n) {                          \
+    static __device__ __noinline__ void mr_##fn##_fix##SUF(const unsigned int n) {                          \
         for (unsigned int k = 0; k < n; k++)                                                           \
             if (!mr_##fn##_inrange(MR_S(k))) MR_R(k) = SLOW(MR_S(k));                                  \
     }
-MR_DEFINE_SCRATCH_BATCH(sin, MR_SLOW_SIN)
-MR_DEFINE_SCRATCH_BATCH(exp, MR_SLOW_EXP)
-MR_DEFINE_SCRATCH_BATCH(log, MR_SLOW_LOG)
+// One instance per segment function (MR_BATCH_HELPERS(_s3)): in a large single unit, helpers shared by
+// every segment are compiled against the generic call ABI and spill; private copies keep the
+// compiler's per-caller register coordination (measured).
+#define MR_BATCH_HELPERS(SUF)                                  \
+    MR_DEFINE_SCRATCH_BATCH_S(sin, MR_SLOW_SIN, SUF)           \
+    MR_DEFINE_SCRATCH_BATCH_S(exp, MR_SLOW_EXP, SUF)           \
+    MR_DEFINE_SCRATCH_BATCH_S(log, MR_SLOW_LOG, SUF)
+#ifndef MR_NO_DEFAULT_BATCH_HELPERS
+MR_BATCH_HELPERS()
+#endif
 #endif  // MR_SCR_STRIDE
 #endif
 

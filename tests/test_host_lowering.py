@@ -141,7 +141,7 @@ def test_transcendental_batching_keeps_values(monkeypatch, form):
         code, consts = r.bytecode()
     assert st["n_sin"] + st["n_exp"] + st["n_ln"] >= 2048
     body = src[src.index("mr_seg0") if "mr_seg0" in src else src.index('extern "C" __global__'):]
-    assert ("_x4(" in body) if form == "registers" else ("_batch(" in body and "MR_R(" in body)
+    assert ("_x4(" in body) if form == "registers" else ("_batch" in body and "MR_R(" in body)
     if form == "separate_units":
         assert st["jit_units"] == st["jit_segments"] + 1 and st["jit_segments"] >= 2 and st["jit_compile_threads"] >= 1
         assert st["link_ms"] > 0 and st["jit_cubin_bytes"] > 1000
