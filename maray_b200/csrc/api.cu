@@ -326,6 +326,7 @@ int nvrtc_compile(maray_cuda* h) {
         "--fmad=false",               // the reference never fuses a*b+c
         "--std=c++17",
         "--ptxas-options=-v",
+        "--diag-suppress=177",        // unused double shadows of boolean values: dead code by design
     };
     // Line tables map SASS to the generated text (ncu source page).  On by default for one unit; a
     // linked build carries one table per unit (4x the cubin, seconds of link time): MARAY_JIT_LINEINFO=1.

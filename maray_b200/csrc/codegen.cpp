@@ -271,6 +271,14 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
     Emitter em{prog, n_trans < opt.inline_transcendentals_below, opt.constants_in_bank ? &bank_index : nullptr};
     const std::vector<uint8_t> booleans = opt.boolean_logic ? find_booleans(prog) : std::vector<uint8_t>();
     if (opt.boolean_logic) em.boolean = &booleans;
+    // The NOT form `1 + -(b)` reads b itself, not only its two operands: b must be visible wherever the
+    // NOT is evaluated (frame slots and imports of segmented programs).
+    auto not_operand = [&](uint32_t id) -> uint32_t {
+        if (booleans.empty() || booleans[id] != 2) return UINT32_MAX;
+        const Node& n = prog.nodes[id];
+        const uint32_t neg = prog.nodes[n.a].op == OP_NEG ? n.a : n.b;
+        return prog.nodes[neg].a;
+    };
     Emitter em_pre = em;                       // prologue kernels compute hoisted values, never load them
     if (hoist) { em.load_kind = &load_kind; em.table_index = &table_index; }
 
@@ -328,6 +336,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
             };
             if (op_is_unary(n.op) || op_is_binary(n.op)) use(n.a);
             if (op_is_binary(n.op)) use(n.b);
+            if (uint32_t extra = not_operand(order[i]); extra != UINT32_MAX) use(extra);
         }
         for (int c = 0; c < 3; c++) {
             Op o = prog.nodes[prog.root[c]].op;
@@ -392,6 +401,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
                     };
                     if (op_is_unary(n.op) || op_is_binary(n.op)) use(n.a);
                     if (op_is_binary(n.op)) use(n.b);
+                    if (uint32_t extra = not_operand(order[i]); extra != UINT32_MAX) use(extra);
                 }
                 std::sort(tmp.begin(), tmp.end());
                 tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());

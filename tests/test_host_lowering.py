@@ -73,6 +73,44 @@ def test_segmented_source_matches_unsegmented(monkeypatch):
     assert bits_equal(a[1], b[1]).all() and np.array_equal(a[0], b[0])
 
 
+def test_boolean_logic_is_value_preserving(monkeypatch, chess_bytes):
+    """0/1-valued values (step, products / min / max of them, 1 - b) are emitted as `bool` logic with a
+    double shadow (codegen.cpp find_booleans).  The text must evaluate to the oracle's bits: with the
+    logic on and off, in one function and cut into segments (booleans crossing a cut travel through the
+    frame as doubles and are re-derived), and on constructions that LOOK boolean but are not: -0.0 as a
+    constant, step of NaN, a product of a boolean with an ordinary value, 1 - x for a non-boolean x."""
+    x, y = E.x(), E.y()
+    inf = E.recip(E.nat(0))
+    nan = E.mul(E.mul(inf, E.nat(0)), E.add(x, E.nat(1)))
+    b1, b2 = E.step(E.sub(x, E.nat(5))), E.step(E.sub(y, E.nat(2)))
+    negzero = E.neg(E.nat(0))
+    tricky = [
+        E.mul(E.add(E.set_xor(b1, b2), E.mul(E.set_inv(b1), E.nat(3))), E.nat(60)),        # NOT feeding arithmetic
+        E.recip(E.add(E.mul(E.min(b1, negzero), E.nat(1)), E.mul(b2, negzero))),            # -0.0 is not a boolean: 1/(+-0)
+        E.add(E.mul(E.max(E.step(nan), E.mul(b1, E.mul(x, E.recip(E.nat(8))))), E.nat(100)),   # step(NaN) = 0; b * value
+              E.mul(E.set_inv(E.mul(x, E.recip(E.nat(16)))), E.nat(50))),                   # 1 - x with x not boolean
+    ]
+    tricky_scene = E.to_bytes([16, 6], tricky)
+    for seg in ("100000", "1500"):
+        for on in ("1", "0"):
+            monkeypatch.setenv("MARAY_JIT_SEGMENT_VALUES", seg)
+            monkeypatch.setenv("MARAY_JIT_BOOLEAN", on)
+            for scene, w, rows in ((chess_bytes, 1024, [511, 512]), (tricky_scene, 16, [0, 2, 5])):
+                with CudaRenderer(gpus=0) as r:
+                    r.load(scene)
+                    st = r.compile("nvrtc")
+                    src = r.source()
+                body = src[src.index("mr_seg0") if "mr_seg0" in src else src.index('extern "C" __global__'):]
+                assert ("const bool b" in body) == (on == "1")
+                if scene is chess_bytes:
+                    assert (st["jit_segments"] > 1) == (seg == "1500")
+                for yrow in rows:
+                    want_rgb, want = _oracle_window(scene, [], 0, w, yrow, yrow + 1)
+                    rgb, planes = host_jit_run(src, w, yrow * w, w)
+                    assert bits_equal(planes, want.reshape(3, w)).all(), (seg, on, yrow)
+                    assert np.array_equal(rgb, want_rgb.reshape(w, 3))
+
+
 def test_let_scoping_and_sharing():
     x, y = E.x(), E.y()
     # Same Let on every channel with different bodies: the canonical compress shape (SURVEY.md F6).
