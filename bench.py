@@ -146,7 +146,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ---- clocks ---------------------------------------------------------------------------------------
@@ -384,13 +384,25 @@ def run_ours(args):
             v, dt, sample = cpu_render_sample(scene_bytes, textures, w, h, args.cpu_sample_s, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                                     "seconds": dt}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     r.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner on stdout when the first communicator is created), so stdout is pointed at stderr for the
+    whole run and the result line goes to a private copy of the original descriptor."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
+    global RESULT_OUT
+    RESULT_OUT = _claim_stdout()
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -45,6 +45,11 @@ struct Gpu {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // pipelined host renders (render_frame_pipelined): one stream + event per row chunk, one copy stream
+    static constexpr int kChunks = 4;
+    cudaStream_t chunk_stream[kChunks] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t chunk_done[kChunks] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
     // band / frame buffer
     uint8_t* d_out = nullptr; size_t out_cap = 0;
     double* d_f64 = nullptr; size_t f64_cap = 0;
@@ -554,6 +559,50 @@ int render_rows_to_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint32_t ya, u
     return MARAY_OK;
 }
 
+// One GPU, frame wanted in host memory, no progress callback: the rows are rendered in kChunks launches
+// on kChunks streams (the tail of one chunk's grid overlaps the head of the next, so cutting the frame
+// costs no wave quantisation) and every chunk is copied out on a separate stream as soon as it is done,
+// while later chunks still render.  What remains exposed of the device->host copy is the last chunk.
+int render_frame_pipelined(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
+    Gpu& g = h->gpus[0];
+    CU_TRY(h, cudaSetDevice(g.device));
+    if (!g.copy_stream) {
+        CU_TRY(h, cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < Gpu::kChunks; c++) {
+            CU_TRY(h, cudaStreamCreateWithFlags(&g.chunk_stream[c], cudaStreamNonBlocking));
+            CU_TRY(h, cudaEventCreateWithFlags(&g.chunk_done[c], cudaEventDisableTiming));
+        }
+    }
+    // chunk boundaries on multiples of 16 rows: every chunk starts 16-byte aligned in the frame
+    uint32_t y[Gpu::kChunks + 1];
+    for (int c = 0; c <= Gpu::kChunks; c++) y[c] = std::min<uint32_t>(hgt, ((uint64_t(hgt) * c / Gpu::kChunks) + 15u) & ~15u);
+    y[0] = 0; y[Gpu::kChunks] = hgt;
+    CU_TRY(h, cudaEventRecord(g.ev0, g.stream));
+    for (int c = 0; c < Gpu::kChunks; c++) {
+        if (y[c + 1] <= y[c]) continue;
+        CU_TRY(h, cudaStreamWaitEvent(g.chunk_stream[c], g.ev0, 0));
+        int rc = launch_band(h, g, w, y[c] * w, (y[c + 1] - y[c]) * w, g.d_out + size_t(y[c]) * w * 3, nullptr, 0, g.chunk_stream[c]);
+        if (rc) return rc;
+        CU_TRY(h, cudaEventRecord(g.chunk_done[c], g.chunk_stream[c]));
+        CU_TRY(h, cudaStreamWaitEvent(g.stream, g.chunk_done[c], 0));
+    }
+    CU_TRY(h, cudaEventRecord(g.ev1, g.stream));          // all chunks rendered
+    double t1 = now_ms();
+    for (int c = 0; c < Gpu::kChunks; c++) {
+        if (y[c + 1] <= y[c]) continue;
+        CU_TRY(h, cudaStreamWaitEvent(g.copy_stream, g.chunk_done[c], 0));
+        CU_TRY(h, cudaMemcpyAsync(host_rgb + size_t(y[c]) * w * 3, g.d_out + size_t(y[c]) * w * 3,
+                                  size_t(y[c + 1] - y[c]) * w * 3, cudaMemcpyDeviceToHost, g.copy_stream));
+    }
+    CU_TRY(h, cudaStreamSynchronize(g.copy_stream));
+    CU_TRY(h, cudaStreamSynchronize(g.stream));
+    float ms = 0.f;
+    CU_TRY(h, cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+    h->stats.kernel_ms[0] = ms;
+    h->stats.d2h_ms = std::max(0.0, (now_ms() - t1) - double(ms));   // what the copies added after the last kernel
+    return MARAY_OK;
+}
+
 int render_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
     int rc = check_renderable(h, w, hgt);
     if (rc) return rc;
@@ -564,7 +613,14 @@ int render_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
     for (double& k : h->stats.kernel_ms) k = 0.0;
     h->stats.gather_ms = 0.0; h->stats.d2h_ms = 0.0;
 
-    if (h->report_kind == MARAY_REPORT_NONE || !h->report_fn || !host_rgb) {
+    const bool hoisting = h->backend == MARAY_BACKEND_NVRTC && (h->jit_ncol || h->jit_nrow);   // its tables are per launch
+    // Opt-in (MARAY_PIPELINE=1): written after this round's GPU budget was spent, so it has run on no GPU yet.
+    const char* pipe_env = std::getenv("MARAY_PIPELINE");
+    if (host_rgb && h->gpus.size() == 1 && !hoisting && pipe_env && std::strtoul(pipe_env, nullptr, 10) != 0 &&
+        (h->report_kind == MARAY_REPORT_NONE || !h->report_fn) && size_t(w) * hgt * 3 >= (size_t(4) << 20)) {
+        rc = render_frame_pipelined(h, w, hgt, host_rgb);
+        if (rc) return rc;
+    } else if (h->report_kind == MARAY_REPORT_NONE || !h->report_fn || !host_rgb) {
         rc = render_rows_to_frame(h, w, hgt, 0, hgt);
         if (rc) return rc;
         if (host_rgb) {
@@ -667,6 +723,11 @@ void maray_cuda_destroy(maray_cuda_t* h) {
         if (g.ev0) cudaEventDestroy(g.ev0);
         if (g.ev1) cudaEventDestroy(g.ev1);
         if (g.stream) cudaStreamDestroy(g.stream);
+        if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
+        for (int c = 0; c < Gpu::kChunks; c++) {
+            if (g.chunk_stream[c]) cudaStreamDestroy(g.chunk_stream[c]);
+            if (g.chunk_done[c]) cudaEventDestroy(g.chunk_done[c]);
+        }
     }
     delete h;
 }
