@@ -602,6 +602,39 @@ mo_scene *mo_open(const uint8_t *bytes, size_t len) {
     return s;
 }
 
+/* maray::save (src/lib.rs:1216-1224) of the scene AFTER var_fixer::fix_color, HEAD layout: lets the
+ * tests compare the fixed trees with the expectations of the reference's own test_var_fixer
+ * (src/lib.rs:1508-1691).  Returns the number of bytes the encoding needs; writes at most cap. */
+typedef struct { uint8_t *p; size_t cap, n; } Wr;
+static void wr_bytes(Wr *w, const void *src, size_t k) {
+    if (w->n + k <= w->cap) memcpy(w->p + w->n, src, k);
+    w->n += k;
+}
+static void wr_u32(Wr *w, uint32_t v) { wr_bytes(w, &v, 4); }   /* little-endian host, like the reader */
+static void wr_u64(Wr *w, uint64_t v) { wr_bytes(w, &v, 8); }
+static void wr_expr(Wr *w, const Expr *e) {
+    wr_u32(w, e->tag);
+    switch (e->tag) {
+    case T_VAR: case T_NAT: wr_u64(w, e->n); break;
+    case T_LET:
+        wr_u64(w, e->ctx->n);
+        for (uint64_t i = 0; i < e->ctx->n; i++) { wr_u64(w, e->ctx->ids[i]); wr_expr(w, e->ctx->defs[i]); }
+        wr_expr(w, e->a);
+        break;
+    case T_DECOR: wr_expr(w, e->a); wr_u64(w, 0); break;          /* tokens were dropped by the reader */
+    case T_APP: wr_u32(w, e->app_id); wr_expr(w, e->a); wr_expr(w, e->b); break;
+    default:
+        if (e->a) wr_expr(w, e->a);
+        if (e->b) wr_expr(w, e->b);
+    }
+}
+size_t mo_fixed_bytes(const mo_scene *s, uint8_t *buf, size_t cap) {
+    Wr w = {buf, buf ? cap : 0, 0};
+    wr_u32(&w, s->size[0]); wr_u32(&w, s->size[1]);
+    for (int i = 0; i < 3; i++) wr_expr(&w, s->color[i]);
+    return w.n;
+}
+
 void mo_close(mo_scene *s) {
     if (!s) return;
     for (uint32_t i = 0; i < s->tex.n; i++) free(s->tex.data[i]);

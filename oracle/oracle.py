@@ -40,6 +40,8 @@ def lib():
         L.mo_tree_nodes.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.mo_set_textures.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p),
                                       ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
+        L.mo_fixed_bytes.restype = ctypes.c_size_t
+        L.mo_fixed_bytes.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         L.mo_eval.restype = ctypes.c_double
         L.mo_eval.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]
         L.mo_render_window.argtypes = [ctypes.c_void_p] + [ctypes.c_uint32] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -76,6 +78,13 @@ class OracleScene:
         ws = (ctypes.c_uint32 * max(n, 1))(*[a.shape[1] for a in arrs])
         hs = (ctypes.c_uint32 * max(n, 1))(*[a.shape[0] for a in arrs])
         lib().mo_set_textures(self._h, n, ptrs, ws, hs)
+
+    def fixed_bytes(self) -> bytes:
+        """`save((size, var_fixer::fix_color(color)))`: the scene as the render loops see it."""
+        n = lib().mo_fixed_bytes(self._h, None, 0)
+        buf = ctypes.create_string_buffer(n)
+        lib().mo_fixed_bytes(self._h, buf, n)
+        return buf.raw
 
     def tree_nodes(self, channel: int) -> int:
         return int(lib().mo_tree_nodes(self._h, channel))

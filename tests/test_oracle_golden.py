@@ -107,3 +107,34 @@ def test_chess_rows_against_reference_png_and_golden(chess_bytes):
         assert np.array_equal(got[i], gold[y]), f"row {y} differs from the committed oracle render"
         if y not in (512, 704):
             assert np.array_equal(got[i], ref_png[y]), f"row {y} differs from images/chess.png"
+
+
+def test_var_fixer_reference_assertions():
+    """The reference's own `test_var_fixer` (src/lib.rs:1508-1691), run against the oracle's restatement of
+    `var_fixer::fix_color` (src/var_fixer.rs:25-82): the scene is opened (which fixes it), written back, and
+    compared with the tree the reference expects."""
+    from maray_b200.expr import add, let_, nat, sub, to_bytes, var_id, x, y
+
+    def fixed(color):
+        return OracleScene(to_bytes([1, 1], color)).fixed_bytes()
+
+    def nest(i0, d0, i1, d1, ref):
+        return let_([(i0, d0)], let_([(i1, d1)], var_id(ref)))
+
+    # one channel three times: {0: x} {0: y} $0  ->  {0: x} {1: y} $1 on every channel (:1520-1571)
+    a = nest(0, x(), 0, y(), 0)
+    b = nest(0, x(), 1, y(), 1)
+    assert fixed([a, a, a]) == to_bytes([1, 1], [b, b, b])
+    # inner definitions differ per channel: fresh ids 1, 2, 3; the shared outer x keeps id 0 (:1573-1631)
+    a2 = [nest(0, x(), 0, add(y(), nat(k)), 0) for k in (1, 2, 3)]
+    b2 = [nest(0, x(), k, add(y(), nat(k)), k) for k in (1, 2, 3)]
+    assert fixed(a2) == to_bytes([1, 1], b2)
+    # both levels differ per channel: ids are handed out in visiting order 0..5 (:1633-1690)
+    a3 = [nest(0, sub(x(), nat(k)), 0, add(y(), nat(k)), 0) for k in (1, 2, 3)]
+    b3 = [nest(2 * k - 2, sub(x(), nat(k)), 2 * k - 1, add(y(), nat(k)), 2 * k - 1) for k in (1, 2, 3)]
+    assert fixed(a3) == to_bytes([1, 1], b3)
+    # the canonical compress shape (one Let, ids 0..n, the same on every channel) is a fixed point
+    from maray_b200 import scenes
+    raw = scenes.chess_1k()
+    size, color, _legacy = E.from_bytes(raw)
+    assert OracleScene(raw).fixed_bytes() == to_bytes(size, color)
