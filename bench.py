@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--backend", default="nvrtc", choices=["nvrtc", "interp"])
     ap.add_argument("--cpu-sample-s", type=float, default=12.0, help="target seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-jit-standin", action="store_true",
+                    help="skip the second CPU baseline (generated straight-line program built with g++, oracle/jit_standin.py)")
     ap.add_argument("--size", default=None, help="WxH override of the workload's frame size (experiments only)")
     return ap.parse_args()
 
@@ -117,6 +119,23 @@ def cpu_render_sample(scene_bytes, textures, w, h, target_s, threads):
     return npx / dt / 1e6, dt, sample
 
 
+def cpu_jit_standin(scene_bytes, textures, w, h, threads, dag_values, target_s=6.0):
+    """Second CPU baseline: a stand-in for the reference's WASM JIT -- the generated
+    straight-line program compiled for the host with g++ -O2 -ffp-contract=off, rows pulled by `threads`
+    workers.  Skipped for programs whose host compile alone would take minutes."""
+    if dag_values > 30000:
+        return {"skipped": f"{dag_values} values: the g++ build alone would exceed the bench budget"}
+    try:
+        from oracle.jit_standin import timed_sample
+        v, dt, sample, compile_s = timed_sample(scene_bytes, textures, w, h, target_s, threads)
+        return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                "what": "stand-in for the reference's WASM JIT: the generated straight-line program built with g++ -O2 "
+                        "-ffp-contract=off (wasmer is not available), one row-pulling thread per core",
+                "sample": sample, "seconds": dt, "compile_s": compile_s}
+    except Exception as exc:          # a missing host compiler must not take the bench line down
+        return {"skipped": f"{type(exc).__name__}: {exc}"[:200]}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path.  The Rust crate cannot
     be built here (no cargo/rustc), so this times oracle/ -- the C restatement of
@@ -146,6 +165,20 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_cpu_jit_standin:
+        from maray_b200 import CudaRenderer
+        with CudaRenderer(gpus=0) as r:
+            r.set_textures(textures)
+            r.load(scene_bytes)
+            os.environ["MARAY_JIT_SOURCE_ONLY"] = "1"
+            try:
+                r.compile("nvrtc")
+            except Exception:
+                pass
+            finally:
+                del os.environ["MARAY_JIT_SOURCE_ONLY"]
+            dag = r.stats()["dag_nodes"]
+        line["cpu_baseline"]["jit_standin"] = cpu_jit_standin(scene_bytes, textures, w, h, threads, dag)
     print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
@@ -384,6 +417,8 @@ def run_ours(args):
             v, dt, sample = cpu_render_sample(scene_bytes, textures, w, h, args.cpu_sample_s, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                                     "seconds": dt}
+            if not args.no_cpu_jit_standin:
+                line["cpu_baseline"]["jit_standin"] = cpu_jit_standin(scene_bytes, textures, w, h, threads, stats["dag_nodes"])
         print(json.dumps(line), file=RESULT_OUT, flush=True)
     r.close()
     if world > 1:

@@ -138,3 +138,24 @@ def test_var_fixer_reference_assertions():
     raw = scenes.chess_1k()
     size, color, _legacy = E.from_bytes(raw)
     assert OracleScene(raw).fixed_bytes() == to_bytes(size, color)
+
+
+def test_jit_standin_cpu_baseline_equals_the_oracle():
+    """bench.py's second CPU baseline (oracle/jit_standin.py: the generated straight-line program built
+    for the host, the stand-in for the reference's WASM JIT) must render what the interpreter restatement
+    renders: same libm, same operations -> identical bytes, on the shipped scene, an SDF scene and a
+    textured one."""
+    from maray_b200 import scenes
+    from oracle.jit_standin import JitStandIn
+
+    tex = scenes.synthetic_textures(2, 64)
+    x, y = E.x(), E.y()
+    textured = E.to_bytes([96, 40], [E.app(E.channel(0, 0), x, y), E.app(E.channel(1, 2), E.sub(x, E.nat(20)), y),
+                                     E.mul(E.app(E.image_width(1), x, y), E.nat(2))])
+    for scene, textures, w, rows in ((scenes.chess_1k(), [], 1024, [0, 512, 704, 1023]),
+                                     (scenes.sdf(320, 200, 12, seed=3), [], 320, [0, 99, 199]),
+                                     (textured, tex, 96, [0, 39])):
+        js = JitStandIn(scene, textures)
+        got = js.render_rows(rows, w, threads=2)
+        want = OracleScene(scene, textures).render_rows(rows, w)
+        assert np.array_equal(got, want)
