@@ -385,7 +385,20 @@ int nvrtc_compile(maray_cuda* h) {
     }
     for (size_t i = 0; i < n_units; i++) {
         if (res[i].rc != NVRTC_SUCCESS) {
-            std::string log = res[i].log;
+            // the diagnostics that matter first: a long log of warnings must not push the errors out of the message
+            std::string log, rest;
+            size_t pos = 0;
+            int keep = 0;
+            while (pos < res[i].log.size()) {
+                size_t nl = res[i].log.find('\n', pos);
+                if (nl == std::string::npos) nl = res[i].log.size();
+                std::string line = res[i].log.substr(pos, nl - pos);
+                if (line.find("error") != std::string::npos) keep = 3;      // the line and the source excerpt after it
+                ((keep > 0) ? log : rest) += line + "\n";
+                if (keep > 0) keep--;
+                pos = nl + 1;
+            }
+            log += rest;
             if (log.size() > 4000) log.resize(4000);
             return fail(h, MARAY_E_COMPILE, "NVRTC (unit " + std::to_string(i) + "): " + nvrtcGetErrorString(res[i].rc) + "\n" + log);
         }
