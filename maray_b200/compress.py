@@ -125,6 +125,19 @@ def is_simple_expr(e: Expr, level: int = 2) -> bool:
     return False
 
 
+_SIMPLE2: Dict[int, bool] = {}      # is_simple_expr(e, 2) per node (nodes are interned and immutable)
+_SIMPLE2_KEEP: List[Expr] = []
+
+
+def _simple2(e: Expr) -> bool:
+    hit = _SIMPLE2.get(id(e))
+    if hit is None:
+        hit = is_simple_expr(e, 2)
+        _SIMPLE2[id(e)] = hit
+        _SIMPLE2_KEEP.append(e)
+    return hit
+
+
 def _count_children(e: Expr) -> Sequence[Expr]:
     """Operands `count_expr` descends into (it does not look inside a `Let`)."""
     if e.tag == E.LET:
@@ -139,23 +152,27 @@ def _count_children(e: Expr) -> Sequence[Expr]:
 def count_terms(root: Expr) -> Tuple[List[Expr], Dict[int, int]]:
     """The compressor's term table for `root`: every sub-term that is not "simple", in the order a
     pre-order walk of the tree first meets it, with its number of occurrences in the tree."""
-    order: List[Expr] = []
+    order: List[Expr] = []      # first-seen pre-order
+    post: List[Expr] = []       # post-order of the same walk: operands before users
     seen = set()
-    stack = [root]
-    while stack:                                   # pre-order, left operand first; a repeated node
-        n = stack.pop()                            # brings nothing new (all below it was seen already)
-        if id(n) in seen or is_simple_expr(n, 2):
+    stack = [(root, False)]
+    while stack:                                   # left operand first; a repeated node brings nothing
+        n, done = stack.pop()                      # new (everything below it was seen the first time)
+        if done:
+            post.append(n)
+            continue
+        if id(n) in seen or _simple2(n):
             continue
         seen.add(id(n))
         order.append(n)
-        kids = _count_children(n)
-        for c in reversed(kids):
-            stack.append(c)
-    # occurrences: multiplicities flow from parents to operands; parents come before operands in any
-    # order sorted by decreasing creation sequence (operands are always created first)
+        stack.append((n, True))
+        for c in reversed(_count_children(n)):
+            stack.append((c, False))
+    # occurrences in the tree: multiplicities flow from users to operands, users first
     occ: Dict[int, int] = {id(n): 0 for n in order}
-    occ[id(root)] = 1 if order and order[0] is root else 0
-    for n in sorted(order, key=lambda v: -v.seq):
+    if order and order[0] is root:
+        occ[id(root)] = 1
+    for n in reversed(post):
         k = occ[id(n)]
         for c in _count_children(n):
             if id(c) in occ:
@@ -211,16 +228,19 @@ class _Compressor:
 
 def rewrite(e: Expr, formulas: Dict[int, int]) -> Expr:
     """`Expr::rewrite`: every occurrence of a definition's formula becomes its variable (checked at a
-    node before its operands are looked at); `Let` nodes are left alone."""
+    node before its operands are looked at); `Let` nodes are left alone.  Nodes without a formula below
+    them are returned as they are."""
     out: Dict[int, Expr] = {}
     for n in E.dag_nodes([e]):
         vid = formulas.get(id(n))
         if vid is not None:
             out[id(n)] = E.var_id(vid)
-        elif n.tag in (E.X, E.Y, E.TAU, E.E, E.NAT, E.VAR, E.LET):
+        elif n.a is None or n.tag == E.LET:
             out[id(n)] = n
         else:
-            out[id(n)] = E._mk(n.tag, out[id(n.a)], out[id(n.b)] if n.b is not None else None, n.n)
+            a = out[id(n.a)]
+            b = out[id(n.b)] if n.b is not None else None
+            out[id(n)] = n if (a is n.a and b is n.b) else E._mk(n.tag, a, b, n.n)
     return out[id(e)]
 
 
@@ -310,5 +330,7 @@ def compress(e: Expr, log=None) -> Expr:
         var_len = len(f"a{vid}")
         ctx.append((vid, formula))
         formulas[id(formula)] = vid
-        res = rewrite(res, formulas)
+        # Only the new formula can still occur: every earlier one was replaced when it was defined, and a
+        # later rewrite cannot re-create it (it would have to contain a variable that did not exist yet).
+        res = rewrite(res, {id(formula): vid})
     return E.let_(ctx, res) if ctx else res
