@@ -73,7 +73,7 @@ typedef struct maray_cuda_stats {
     uint32_t jit_units;           /* translation units compiled (1, or 1 + segments when linked)     */
     uint32_t jit_compile_threads; /* host threads that ran NVRTC concurrently (0 on a cache hit)     */
     uint32_t jit_cache_hit;       /* 1 when the cubin came from the MARAY_JIT_CACHE directory        */
-    uint32_t reserved0;
+    uint32_t interp_uniform_slots;/* per-block row-uniform slots (interpreter, MARAY_INTERP_UNIFORM=1; else 0) */
     /* timings, milliseconds */
     double lower_ms;              /* Expr -> SSA                                                     */
     double codegen_ms;            /* SSA -> source / bytecode                                        */

@@ -63,6 +63,7 @@ struct Gpu {
     double* d_colv = nullptr; size_t colv_cap = 0;     // hoisting tables (doubles)
     double* d_rowv = nullptr; size_t rowv_cap = 0;
     uint64_t* d_code = nullptr;
+    uint64_t* d_code_uni = nullptr;   // row-uniform form of the bytecode (MARAY_INTERP_UNIFORM=1)
     double* d_consts = nullptr;
     double* d_sink = nullptr;
     bool peer_to_0 = false;
@@ -85,6 +86,11 @@ struct maray_cuda {
     std::vector<char> cubin;
     Bytecode bc;
     unsigned interp_block = 128, interp_ppt = 2;
+    // Opt-in (MARAY_INTERP_UNIFORM=1), written after this round's GPU budget was spent -- run on no GPU yet:
+    // the row-uniform bytecode and its launch shape; used for launches whose blocks lie inside one row.
+    Bytecode bc_uni;
+    bool have_uni = false;
+    unsigned interp_block_uni = 0, interp_ppt_uni = 0;
     unsigned jit_block = 256;
     unsigned jit_dyn_smem = 0;                         // dynamic shared memory of the generated kernel
     unsigned jit_maxreg = 0;
@@ -119,6 +125,7 @@ void release_backend(maray_cuda* h) {
         if (g.d_colv) { cudaFree(g.d_colv); g.d_colv = nullptr; g.colv_cap = 0; }
         if (g.d_rowv) { cudaFree(g.d_rowv); g.d_rowv = nullptr; g.rowv_cap = 0; }
         if (g.d_code) { cudaFree(g.d_code); g.d_code = nullptr; }
+        if (g.d_code_uni) { cudaFree(g.d_code_uni); g.d_code_uni = nullptr; }
         if (g.d_consts) { cudaFree(g.d_consts); g.d_consts = nullptr; }
     }
     h->compiled = false;
@@ -516,8 +523,14 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
         unsigned grid = (n + h->jit_block - 1) / h->jit_block;
         CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, h->jit_dyn_smem, stream));
     } else {
-        CU_TRY(h, launch_interp(p, g.d_code, unsigned(h->bc.code.size()), g.d_consts, unsigned(h->bc.consts.size()),
-                                h->bc.n_slots, h->interp_block, h->interp_ppt, stream));
+        const unsigned span_uni = h->interp_block_uni * h->interp_ppt_uni;
+        if (h->have_uni && g.d_code_uni && span_uni && w % span_uni == 0 && p0 % span_uni == 0) {
+            CU_TRY(h, launch_interp(p, g.d_code_uni, unsigned(h->bc_uni.code.size()), g.d_consts, unsigned(h->bc_uni.consts.size()),
+                                    h->bc_uni.n_slots, h->interp_block_uni, h->interp_ppt_uni, stream, h->bc_uni.n_uniform, true));
+        } else {
+            CU_TRY(h, launch_interp(p, g.d_code, unsigned(h->bc.code.size()), g.d_consts, unsigned(h->bc.consts.size()),
+                                    h->bc.n_slots, h->interp_block, h->interp_ppt, stream));
+        }
     }
     return MARAY_OK;
 }
@@ -861,9 +874,27 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         if (!h->interp_block)
             return fail(h, MARAY_E_UNSUPPORTED, "program needs " + std::to_string(h->bc.n_slots) +
                                                     " live values per pixel, more than the interpreter's shared-memory slot file holds");
+        h->have_uni = false;
+        h->stats.interp_uniform_slots = 0;
+        if (const char* e = std::getenv("MARAY_INTERP_UNIFORM")) {
+            if (std::strtoul(e, nullptr, 10) != 0) {
+                if (!compile_bytecode(h->prog, &h->bc_uni, &err, true)) return fail(h, MARAY_E_COMPILE, err);
+                if (h->bc_uni.code.size() & 1) h->bc_uni.code.push_back(bc_encode(BC_END, 0, 0, 0, 0));
+                // same constants in the same order as the per-pixel form: the device copy is shared
+                const unsigned shapes[][2] = {{256, 2}, {256, 1}, {128, 1}, {64, 1}, {32, 1}};
+                h->interp_block_uni = 0;
+                for (auto& sh : shapes)
+                    if (interp_smem_bytes(sh[0], sh[1], h->bc_uni.n_slots, unsigned(h->bc_uni.consts.size()), h->bc_uni.n_uniform) <= 200 * 1024) {
+                        h->interp_block_uni = sh[0]; h->interp_ppt_uni = sh[1];
+                        break;
+                    }
+                h->have_uni = h->interp_block_uni != 0 && h->bc_uni.consts == h->bc.consts;
+                if (h->have_uni) h->stats.interp_uniform_slots = h->bc_uni.n_uniform;
+            }
+        }
         h->stats.codegen_ms = now_ms() - t1;
         h->stats.interp_instructions = uint32_t(h->bc.code.size());
-        h->stats.interp_slots = h->bc.n_slots;
+        h->stats.interp_slots = h->have_uni ? h->bc_uni.n_slots : h->bc.n_slots;
     }
     h->backend = backend;
 
@@ -887,6 +918,10 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
             } else {
                 CU_TRY(h, cudaMalloc(&g.d_code, h->bc.code.size() * sizeof(uint64_t)));
                 CU_TRY(h, cudaMemcpy(g.d_code, h->bc.code.data(), h->bc.code.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+                if (h->have_uni) {
+                    CU_TRY(h, cudaMalloc(&g.d_code_uni, h->bc_uni.code.size() * sizeof(uint64_t)));
+                    CU_TRY(h, cudaMemcpy(g.d_code_uni, h->bc_uni.code.data(), h->bc_uni.code.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+                }
                 CU_TRY(h, cudaMalloc(&g.d_consts, h->bc.consts.size() * sizeof(double)));
                 CU_TRY(h, cudaMemcpy(g.d_consts, h->bc.consts.data(), h->bc.consts.size() * sizeof(double), cudaMemcpyHostToDevice));
             }
@@ -983,10 +1018,11 @@ int maray_cuda_get_source(const maray_cuda_t* h, char* buf, size_t cap, size_t* 
 int maray_cuda_get_bytecode(const maray_cuda_t* h, uint64_t* code, size_t cap_instr, size_t* n_instr, double* consts,
                             size_t cap_consts, size_t* n_consts) {
     if (!h) return MARAY_E_INVALID;
-    if (n_instr) *n_instr = h->bc.code.size();
-    if (n_consts) *n_consts = h->bc.consts.size();
-    if (code) std::memcpy(code, h->bc.code.data(), std::min(cap_instr, h->bc.code.size()) * sizeof(uint64_t));
-    if (consts) std::memcpy(consts, h->bc.consts.data(), std::min(cap_consts, h->bc.consts.size()) * sizeof(double));
+    const Bytecode& bc = h->have_uni ? h->bc_uni : h->bc;   // with MARAY_INTERP_UNIFORM=1: the row-uniform form
+    if (n_instr) *n_instr = bc.code.size();
+    if (n_consts) *n_consts = bc.consts.size();
+    if (code) std::memcpy(code, bc.code.data(), std::min(cap_instr, bc.code.size()) * sizeof(uint64_t));
+    if (consts) std::memcpy(consts, bc.consts.data(), std::min(cap_consts, bc.consts.size()) * sizeof(double));
     return MARAY_OK;
 }
 

@@ -14,13 +14,14 @@ constexpr uint32_t NONE = 0xffffffffu;
 
 class BcGen {
 public:
-    BcGen(const Program& p, Bytecode& b) : P(p), B(b) {}
+    BcGen(const Program& p, Bytecode& b, bool row_uniform) : P(p), B(b), uniform(row_uniform) {}
     std::string err;
 
     void run() {
         const size_t n = P.nodes.size();
         uses_left.assign(n, 0);
         slot.assign(n, -1);
+        uslot.assign(n, -1);
         kidx.assign(n, -1);
         for (size_t i = 0; i < n; i++) {
             const Node& nd = P.nodes[i];
@@ -40,6 +41,7 @@ public:
             if (P.nodes[i].op == OP_Y) { slot[i] = 1; uses_left[i] = 0x7fffffff; }
         }
         B.n_slots = 2;
+        B.n_uniform = 0;
 
         const std::vector<uint32_t>& order = P.order;
         for (size_t i = 0; i < order.size() && err.empty(); i++) {
@@ -68,13 +70,18 @@ private:
     const Program& P;
     Bytecode& B;
     std::vector<uint32_t> uses_left;
-    std::vector<int32_t> slot, kidx;
+    const bool uniform;              // y-only values go to row-uniform slots
+    std::vector<int32_t> slot, uslot, kidx;
     std::vector<uint32_t> free_slots;
     uint32_t acc_holds = NONE;
     int32_t last_stored = -1;        // slot written by the previous instruction, or -1
+    int32_t last_stored_uni = -1;    // uniform slot written by the previous instruction, or -1
 
     bool is_const(uint32_t id) const { return P.nodes[id].op == OP_CONST; }
     bool has_slot(uint32_t id) const { return slot[id] >= 0; }
+    bool has_uslot(uint32_t id) const { return uslot[id] >= 0; }
+    // y-only values (not Y itself, which is preloaded per pixel) are row-uniform
+    bool row_uniform_value(uint32_t id) const { return uniform && P.nodes[id].dep == DEP_Y && P.nodes[id].op != OP_Y; }
 
     uint32_t alloc_slot() {
         if (!free_slots.empty()) { uint32_t s = free_slots.back(); free_slots.pop_back(); return s; }
@@ -84,12 +91,21 @@ private:
     void emit(BcOp op, uint32_t flags, uint32_t dst, uint32_t a, uint32_t b) {
         B.code.push_back(bc_encode(op, flags, dst, a, b));
         last_stored = -1;
+        last_stored_uni = -1;
     }
     // The instruction just emitted produced the accumulator value: make it also store to a slot.
     uint32_t store_last() {
         uint32_t s = alloc_slot();
         B.code.back() |= (uint64_t(BC_F_STORE) << 8) | (uint64_t(s) << 16);
         last_stored = int32_t(s);
+        return s;
+    }
+    // Same, to a fresh row-uniform slot (never recycled: other warps of the block may still read it).
+    uint32_t store_last_uniform() {
+        if (B.n_uniform >= 65535) { err = "program needs more than 65535 row-uniform values"; return 0; }
+        uint32_t s = B.n_uniform++;
+        B.code.back() |= (uint64_t(BC_F_STORE | BC_F_ST_UNI) << 8) | (uint64_t(s) << 16);
+        last_stored_uni = int32_t(s);
         return s;
     }
     void consume(uint32_t id) {
@@ -111,12 +127,19 @@ private:
     bool first_fields(uint32_t v, uint32_t* flags, uint32_t* a) {
         if (acc_holds == v && !is_const(v)) { *flags |= BC_F_ACC_A; *a = 0; return true; }
         if (has_slot(v)) { *a = uint32_t(slot[v]); return true; }
+        if (has_uslot(v)) { *flags |= BC_F_A_UNI; *a = uint32_t(uslot[v]); return true; }
         err = "internal: first operand is neither in the accumulator nor in a slot";
         return false;
     }
     // Operand fields for `second` (slot, constant, or the value the previous instruction stored).
     bool second_fields(uint32_t v, uint32_t* flags, uint32_t* b) {
         if (is_const(v)) { *flags |= BC_F_B_CONST; *b = uint32_t(kidx[v]); return true; }
+        if (has_uslot(v)) {
+            *flags |= BC_F_B_UNI;
+            *b = uint32_t(uslot[v]);
+            if (uslot[v] == last_stored_uni) *flags |= BC_F_FWD_B;
+            return true;
+        }
         if (!has_slot(v)) { err = "internal: second operand is not in a slot"; return false; }
         *b = uint32_t(slot[v]);
         if (slot[v] == last_stored) *flags |= BC_F_FWD_B;
@@ -175,7 +198,8 @@ private:
         // A slot is needed unless the only remaining reader is the next instruction via the accumulator.
         if (other_uses > 1 || (other_uses == 1 && !next_takes_from_acc(id, next))) {
             if (n.op == OP_TEX) emit(BC_MOV, BC_F_ACC_A, 0, 0, 0);   // TEX uses the dst field for its texture id
-            slot[id] = int32_t(store_last());
+            if (row_uniform_value(id)) uslot[id] = int32_t(store_last_uniform());
+            else slot[id] = int32_t(store_last());
         }
         // channel outputs are written the moment their value exists
         for (int c = 0; c < 3; c++) {
@@ -189,10 +213,10 @@ private:
 
 }  // namespace
 
-bool compile_bytecode(const Program& prog, Bytecode* out, std::string* err) {
+bool compile_bytecode(const Program& prog, Bytecode* out, std::string* err, bool row_uniform) {
     out->code.clear();
     out->consts.clear();
-    BcGen g(prog, *out);
+    BcGen g(prog, *out, row_uniform);
     g.run();
     if (!g.err.empty()) { if (err) *err = g.err; return false; }
     if (out->consts.empty()) out->consts.push_back(0.0);

@@ -43,11 +43,20 @@ constexpr uint32_t BC_F_ACC_A = 2u;      // first operand is the accumulator
 constexpr uint32_t BC_F_SWAP = 4u;       // compute op(second, first)
 constexpr uint32_t BC_F_B_CONST = 8u;    // second operand is constant[b]
 constexpr uint32_t BC_F_FWD_B = 16u;     // second operand is the accumulator (slot b was stored by the previous instruction)
+// Row-uniform slots (optional form, compile_bytecode(.., row_uniform = true)): a value that depends on y
+// only is the same for every pixel of a row, so when every block of a launch lies inside one row it
+// needs ONE word per block, not one per thread.  Uniform slots are numbered separately and never
+// recycled: every warp computes and stores every such value itself (same bits), so a warp only ever
+// reads what it has written and no barrier is needed.
+constexpr uint32_t BC_F_A_UNI = 32u;     // first operand is uniform slot a
+constexpr uint32_t BC_F_B_UNI = 64u;     // second operand is uniform slot b
+constexpr uint32_t BC_F_ST_UNI = 128u;   // the store (BC_F_STORE) goes to uniform slot dst
 
 struct Bytecode {
     std::vector<uint64_t> code;      // ends with BC_END
     std::vector<double> consts;
-    uint32_t n_slots = 2;            // including X and Y
+    uint32_t n_slots = 2;            // per-pixel slots, including X and Y
+    uint32_t n_uniform = 0;          // per-block slots (row-uniform form only)
 };
 
 inline uint64_t bc_encode(BcOp op, uint32_t flags, uint32_t dst, uint32_t a, uint32_t b) {
@@ -55,6 +64,6 @@ inline uint64_t bc_encode(BcOp op, uint32_t flags, uint32_t dst, uint32_t a, uin
            (uint64_t(b & 0xffff) << 48);
 }
 
-bool compile_bytecode(const Program& prog, Bytecode* out, std::string* err);
+bool compile_bytecode(const Program& prog, Bytecode* out, std::string* err, bool row_uniform = false);
 
 }  // namespace maray

@@ -41,17 +41,25 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // (Measured and rejected: moving sqrt/1/x/sin/exp/ln/texture bodies out of line to shrink the loop --
 // chess_1k 37.3 vs 40.6 ms, but the transcendental-heavy deep scene 28.9 vs 23.5 ms.)
-template <int P>
+//
+// U = true is the row-uniform form of the bytecode (bytecode.hpp, BC_F_*_UNI): values that depend on y
+// only live in n_uniform per-BLOCK words placed after the constants; every block of such a launch lies
+// inside one image row (the host checks it).  Every warp computes and stores every uniform value itself
+// with identical bits and uniform slots are never recycled, so no barrier is needed.  With U = false
+// none of that code exists in the kernel.
+template <int P, bool U>
 __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code, unsigned int n_instr,
-                             const double* __restrict__ consts, unsigned int n_consts, unsigned int n_slots) {
+                             const double* __restrict__ consts, unsigned int n_consts, unsigned int n_slots,
+                             unsigned int n_uniform) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [2][kChunk] instruction words | staging tile (3*B*P bytes, 16-aligned) | constants | slots
+    // layout: [2][kChunk] instruction words | staging tile (3*B*P bytes, 16-aligned) | constants | uniform slots | slots
     uint64_t* code_s = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned char* stage = smem_raw + 2 * kChunk * sizeof(uint64_t);
     const unsigned int B = blockDim.x;
     const unsigned int tid = threadIdx.x;
     double* consts_s = reinterpret_cast<double*>(stage + ((3u * B * P + 15u) & ~15u));
-    double* slots = consts_s + ((n_consts + 1u) & ~1u);
+    double* uslots = consts_s + ((n_consts + 1u) & ~1u);
+    double* slots = uslots + (U ? ((n_uniform + 1u) & ~1u) : 0u);
 
     const unsigned int first = blockIdx.x * B * P;
     double acc[P], va[P], vb[P];
@@ -83,9 +91,13 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
         const bool bk = (w >> 8) & BC_F_B_CONST;
         const double* pa = slots + (size_t)a * P * B + tid;
         const double* pb = bk ? consts_s + b : slots + (size_t)b * P * B + tid;
-        const unsigned int sb = bk ? 0u : B;
+        unsigned int sa = B, sb = bk ? 0u : B;
+        if constexpr (U) {
+            if ((w >> 8) & BC_F_A_UNI) { pa = uslots + a; sa = 0u; }
+            if ((w >> 8) & BC_F_B_UNI) { pb = uslots + b; sb = 0u; }
+        }
 #pragma unroll
-        for (int k = 0; k < P; k++) { fa[k] = pa[k * B]; fb[k] = pb[k * sb]; }
+        for (int k = 0; k < P; k++) { fa[k] = pa[k * sa]; fb[k] = pb[k * sb]; }
     };
 
     for (unsigned int c = 0; c < n_chunks; c++) {
@@ -183,9 +195,15 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
                 }
             }
             if (fl & BC_F_STORE) {
-                double* dp = slots + (size_t)(lo >> 16) * P * B + tid;
+                bool uni = false;
+                if constexpr (U) uni = (fl & BC_F_ST_UNI) != 0;
+                if (uni) {
+                    uslots[lo >> 16] = acc[0];       // the same bits in every thread and for every k: one row
+                } else {
+                    double* dp = slots + (size_t)(lo >> 16) * P * B + tid;
 #pragma unroll
-                for (int k = 0; k < P; k++) dp[k * B] = acc[k];
+                    for (int k = 0; k < P; k++) dp[k * B] = acc[k];
+                }
             }
             w = wn;
 #pragma unroll
@@ -220,39 +238,47 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
     }
 }
 
-size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_slots, unsigned int n_consts) {
+size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_slots, unsigned int n_consts,
+                         unsigned int n_uniform) {
     size_t stage = (3u * (size_t)block * pixels_per_thread + 15u) & ~size_t(15);
     return 2 * kChunk * sizeof(uint64_t) + stage + (size_t)((n_consts + 1u) & ~1u) * sizeof(double) +
+           (size_t)((n_uniform + 1u) & ~1u) * sizeof(double) +
            (size_t)(n_slots + 3u) * pixels_per_thread * block * sizeof(double);   // + 3 channel-output slots
+}
+
+template <int P, bool U>
+static cudaError_t launch_interp_as(const MrParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
+                                    unsigned int n_consts, unsigned int n_slots, unsigned int n_uniform, unsigned int block,
+                                    unsigned int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(maray_interp<P, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    maray_interp<P, U><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_interp(const MrParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
                           unsigned int n_consts, unsigned int n_slots, unsigned int block, unsigned int pixels_per_thread,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, unsigned int n_uniform, bool row_uniform) {
     if (p.n == 0) return cudaSuccess;
-    size_t smem = interp_smem_bytes(block, pixels_per_thread, n_slots, n_consts);
+    size_t smem = interp_smem_bytes(block, pixels_per_thread, n_slots, n_consts, row_uniform ? n_uniform : 0u);
     unsigned int span = block * pixels_per_thread;
     unsigned int grid = (p.n + span - 1) / span;
-    cudaError_t e;
+    if (row_uniform) {
+        // every block must lie inside one image row
+        if (p.W % span != 0 || p.p0 % span != 0) return cudaErrorInvalidValue;
+        switch (pixels_per_thread) {
+        case 1: return launch_interp_as<1, true>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform, block, grid, smem, stream);
+        case 2: return launch_interp_as<2, true>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform, block, grid, smem, stream);
+        case 4: return launch_interp_as<4, true>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform, block, grid, smem, stream);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (pixels_per_thread) {
-    case 1:
-        e = cudaFuncSetAttribute(maray_interp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        maray_interp<1><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_slots);
-        break;
-    case 2:
-        e = cudaFuncSetAttribute(maray_interp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        maray_interp<2><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_slots);
-        break;
-    case 4:
-        e = cudaFuncSetAttribute(maray_interp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        maray_interp<4><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_slots);
-        break;
+    case 1: return launch_interp_as<1, false>(p, d_code, n_instr, d_consts, n_consts, n_slots, 0u, block, grid, smem, stream);
+    case 2: return launch_interp_as<2, false>(p, d_code, n_instr, d_consts, n_consts, n_slots, 0u, block, grid, smem, stream);
+    case 4: return launch_interp_as<4, false>(p, d_code, n_instr, d_consts, n_consts, n_slots, 0u, block, grid, smem, stream);
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -127,6 +127,7 @@ def host_jit_run(source: str, w: int, p0: int, n: int, textures=()):
 (BC_END, BC_MOV, BC_ADD, BC_MUL, BC_MAX, BC_MIN, BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,
  BC_TEX, BC_OUT_R, BC_OUT_G, BC_OUT_B) = range(18)
 F_STORE, F_ACC_A, F_SWAP, F_B_CONST, F_FWD_B = 1, 2, 4, 8, 16
+F_A_UNI, F_B_UNI, F_ST_UNI = 32, 64, 128
 
 
 def _vec(fn):
@@ -183,14 +184,21 @@ def bytecode_run(code, consts, xs, ys, textures=()):
     ys = np.asarray(ys, dtype=np.float64)
     n = xs.shape[0]
     slots = {0: xs, 1: ys}
+    # Row-uniform form (bytecode.hpp BC_F_*_UNI): one word per BLOCK.  The kernel's blocks lie inside one
+    # row, so the pixels given here must share one y; the uniform word is read from / written by pixel 0
+    # and asserted to be the same for every pixel -- a value wrongly classified as row-uniform fails here.
+    uslots = {}
     zero = np.zeros(n)
     acc = np.zeros(n)
     out = np.zeros((3, n))
 
     def fetch(w):
         fl, a, b = (w >> 8) & 0xFF, (w >> 32) & 0xFFFF, (w >> 48) & 0xFFFF
-        fa = slots.get(a, zero)
-        fb = np.full(n, consts[b]) if fl & F_B_CONST else slots.get(b, zero)
+        fa = np.full(n, uslots.get(a, 0.0)) if fl & F_A_UNI else slots.get(a, zero)
+        if fl & F_B_CONST:
+            fb = np.full(n, consts[b])
+        else:
+            fb = np.full(n, uslots.get(b, 0.0)) if fl & F_B_UNI else slots.get(b, zero)
         return fa, fb
 
     words = [int(w) for w in code]
@@ -225,7 +233,13 @@ def bytecode_run(code, consts, xs, ys, textures=()):
                 raise ValueError(f"bad opcode {op}")
             if fl & F_STORE:
                 assert op != BC_TEX, "TEX keeps its texture id in the dst field and must not store"
-                slots[dst] = acc
+                if fl & F_ST_UNI:
+                    assert np.unique(ys).size == 1, "row-uniform bytecode must be run one row at a time"
+                    assert bits_equal(acc, np.full(n, acc[0])).all(), "a row-uniform slot got a value that varies along the row"
+                    assert dst not in uslots, "row-uniform slots are never recycled"
+                    uslots[dst] = float(acc[0])
+                else:
+                    slots[dst] = acc
             va, vb = nxt
     return out
 

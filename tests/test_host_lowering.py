@@ -114,6 +114,37 @@ def test_boolean_logic_is_value_preserving(monkeypatch, chess_bytes):
                     assert np.array_equal(rgb, want_rgb.reshape(w, 3))
 
 
+def test_row_uniform_bytecode_form(monkeypatch, chess_bytes):
+    """MARAY_INTERP_UNIFORM=1 (opt-in): y-only values live in per-block words.  The bytecode must still
+    evaluate to the oracle's bits (numpy reader, one row at a time, which also checks that every
+    "row-uniform" store really is the same along the row and that uniform slots are never recycled),
+    and the per-pixel slot file must shrink -- chess keeps 59 y-only values live at its peak."""
+    with CudaRenderer(gpus=0) as r:
+        r.load(chess_bytes)
+        plain = r.compile("interp")
+    monkeypatch.setenv("MARAY_INTERP_UNIFORM", "1")
+    tex = scenes.synthetic_textures(1, 32)
+    x, y = E.x(), E.y()
+    mixed = E.to_bytes([40, 6], [E.add(E.mul(E.sin(E.mul(y, E.nat(3))), x), E.app(E.channel(0, 1), x, E.mul(y, E.nat(2)))),
+                                 E.max(E.step(E.sub(y, E.nat(2))), E.mul(E.sqrt(y), E.recip(E.add(x, E.nat(1))))),
+                                 E.mul(E.exp(E.neg(y)), E.nat(200))])                  # third channel: y-only root
+    for scene, textures, w, rows in ((chess_bytes, [], 1024, [0, 512, 704]), (scenes.sdf(320, 200, 12, seed=3), [], 320, [7, 150]),
+                                     (mixed, tex, 40, [0, 3, 5])):
+        with CudaRenderer(gpus=0) as r:
+            r.set_textures(textures)
+            r.load(scene)
+            st = r.compile("interp")
+            code, consts = r.bytecode()
+        flags = (code >> np.uint64(8)) & np.uint64(0xFF)
+        assert st["interp_uniform_slots"] > 0 and (flags & np.uint64(128)).any()
+        if scene is chess_bytes:
+            assert plain["interp_slots"] == 86 and st["interp_slots"] <= 40 and plain["interp_uniform_slots"] == 0
+        for yrow in rows:
+            _rgb, want = _oracle_window(scene, textures, 0, w, yrow, yrow + 1)
+            got = bytecode_run(code, consts, np.arange(w), np.full(w, yrow), textures)
+            assert bits_equal(got, want.reshape(3, w)).all(), yrow
+
+
 def test_let_scoping_and_sharing():
     x, y = E.x(), E.y()
     # Same Let on every channel with different bodies: the canonical compress shape (SURVEY.md F6).
