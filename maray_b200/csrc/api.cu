@@ -524,7 +524,8 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
         CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, h->jit_dyn_smem, stream));
     } else {
         const unsigned span_uni = h->interp_block_uni * h->interp_ppt_uni;
-        if (h->have_uni && g.d_code_uni && span_uni && w % span_uni == 0 && p0 % span_uni == 0) {
+        // blocks inside one row, and no idle lanes (an idle lane re-evaluates pixel p0, whose row may differ)
+        if (h->have_uni && g.d_code_uni && span_uni && w % span_uni == 0 && p0 % span_uni == 0 && n % span_uni == 0) {
             CU_TRY(h, launch_interp(p, g.d_code_uni, unsigned(h->bc_uni.code.size()), g.d_consts, unsigned(h->bc_uni.consts.size()),
                                     h->bc_uni.n_slots, h->interp_block_uni, h->interp_ppt_uni, stream, h->bc_uni.n_uniform, true));
         } else {

@@ -264,8 +264,8 @@ cudaError_t launch_interp(const MrParams& p, const uint64_t* d_code, unsigned in
     unsigned int span = block * pixels_per_thread;
     unsigned int grid = (p.n + span - 1) / span;
     if (row_uniform) {
-        // every block must lie inside one image row
-        if (p.W % span != 0 || p.p0 % span != 0) return cudaErrorInvalidValue;
+        // every block must lie inside one image row, and there must be no idle lanes (they redo pixel p0)
+        if (p.W % span != 0 || p.p0 % span != 0 || p.n % span != 0) return cudaErrorInvalidValue;
         switch (pixels_per_thread) {
         case 1: return launch_interp_as<1, true>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform, block, grid, smem, stream);
         case 2: return launch_interp_as<2, true>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform, block, grid, smem, stream);
