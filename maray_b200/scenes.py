@@ -256,6 +256,37 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
     return E.to_bytes([w, h], E.share_let(chans, bind=named))
 
 
+# ---- the reference's example programs, re-run through the restated tooling -------------------------
+def example_test_rs() -> bytes:
+    """examples/test.rs:7-31: a rounded box XOR a circle at 512x512, `simplify` then `compressor::compress`,
+    every channel `shape * 255` -- built with the DSL mirror and the restated simplify/compress."""
+    from . import compress as C
+    from . import simplify as S
+
+    size = [512, 512]
+    p = [E.div(E.x(), E.nat(size[0])), E.div(E.y(), E.nat(size[1]))]
+    center = [E.half(), E.half()]
+    tenth = E.div(E.nat(1), E.nat(10))
+    box = E.sd_inside(E.sd_rounded_box([E.div(E.half(), E.nat(2)), E.half()], E.p4_same(tenth))).translate(center)
+    circle = E.sd_inside(E.sd_circle(E.recip(E.nat(3)))).translate(center)
+    shape = C.compress(S.simplify(E.set_xor(box, circle).subst2(p)))
+    ch = E.mul(shape, E.nat(255))
+    return E.to_bytes(size, [ch, ch, ch])
+
+
+def example_test6_rs() -> bytes:
+    """examples/test6.rs: the three channels of texture 0, the blue one flipped with `nat(1024) - y()`."""
+    color = [E.app(E.channel(0, 0), E.x(), E.y()), E.app(E.channel(0, 1), E.x(), E.y()),
+             E.app(E.channel(0, 2), E.x(), E.nat(1024) - E.y())]
+    return E.to_bytes([1024, 1024], color)
+
+
+def example_test7_rs() -> bytes:
+    """examples/test7.rs: `nat(255) * x() / nat(128)` on every channel, 128x128."""
+    e = E.nat(255) * E.x() / E.nat(128)
+    return E.to_bytes([128, 128], [e, e, e])
+
+
 def by_name(name: str) -> Tuple[bytes, List[np.ndarray], Tuple[int, int]]:
     """(maray bytes, textures, (w, h)) for a workload name used by bench.py and the tests."""
     if name == "chess_1k":

@@ -145,6 +145,26 @@ def test_row_uniform_bytecode_form(monkeypatch, chess_bytes):
             assert bits_equal(got, want.reshape(3, w)).all(), yrow
 
 
+def test_reference_example_programs():
+    """The reference's examples/test.rs, test6.rs and test7.rs re-authored with the DSL mirror (test.rs goes
+    through the restated simplify + compress): both back ends' host-checkable forms must evaluate to the
+    oracle's bits, and test.rs must come out as the four-definition formula the compressor finds."""
+    from maray_b200 import compress as C
+    scene = scenes.example_test_rs()
+    _size, color, _ = E.from_bytes(scene)
+    shape = color[0].a
+    assert shape.tag == E.LET and len(shape.vars) == 4
+    assert C.fmt(shape.a) == "max(min($2,1-$3),min($3,1-$2))"
+    assert C.fmt(shape.vars[3][1]) == "step(1/3-sqrt((x/512-1/2)^2+(y/512-1/2)^2))"
+    _check_scene(scene, 512, [0, 100, 256, 400])
+    rgb = OracleScene(scene).render_rows([256], 512)[0]
+    # the centre row: outside both shapes, inside the circle only, inside both (XOR = 0)
+    assert set(int(v) for v in np.unique(rgb)) == {0, 255} and rgb[10, 0] == 0 and rgb[100, 0] == 255 and rgb[256, 0] == 0
+    tex = scenes.synthetic_textures(1, 64)
+    _check_scene(scenes.example_test6_rs(), 1024, [0, 33, 1023], tex)
+    _check_scene(scenes.example_test7_rs(), 128, [0, 127])
+
+
 def test_let_scoping_and_sharing():
     x, y = E.x(), E.y()
     # Same Let on every channel with different bodies: the canonical compress shape (SURVEY.md F6).
