@@ -7,6 +7,7 @@
 //   one device->host copy hands the frame to the caller.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nvrtc.h>
 
 #include <algorithm>
@@ -318,7 +319,8 @@ bool cache_load(const std::string& path, std::vector<char>* cubin, uint32_t* reg
 }
 
 void cache_store(const std::string& path, const std::vector<char>& cubin, uint32_t registers, uint32_t units) {
-    std::string tmp = path + ".tmp" + std::to_string((unsigned long long)now_ms());
+    // several processes may finish the same scene at the same time (one rank per GPU): private temporary names
+    std::string tmp = path + ".tmp" + std::to_string((unsigned long long)getpid()) + "_" + std::to_string((unsigned long long)now_ms());
     FILE* f = std::fopen(tmp.c_str(), "wb");
     if (!f) return;
     CacheHeader hd;
