@@ -264,3 +264,62 @@ def test_cubin_cache_round_trip(monkeypatch, tmp_path):
         r.load(scene)
         assert r.compile("nvrtc")["jit_cache_hit"] == 0
     assert len(list(tmp_path.glob("*.mrcubin"))) == 2
+
+
+def _random_scene(seed: int, w: int, h: int, n_values: int):
+    """Seeded random DAG over every non-transcendental operation, rich in the shapes the boolean logic and
+    the segment cuts care about: steps, 1 - b, products / min / max of booleans and of ordinary values,
+    negated booleans, +-0, infinities and NaN (1/0, inf - inf), values shared across channels."""
+    rng = scenes.Lcg(seed)
+    x, y = E.x(), E.y()
+    pool = [x, y, E.div(x, E.nat(w)), E.div(y, E.nat(h)), E.sub(x, E.nat(rng.between(1, w - 1))),
+            E.sub(y, E.nat(rng.between(0, h - 1))), E.nat(0), E.nat(1), E.neg(E.nat(0)), E.recip(E.nat(0))]
+    bools = []
+    for _ in range(n_values):
+        k = rng.below(100)
+        a = pool[rng.below(len(pool))]
+        b = pool[rng.below(len(pool))]
+        if k < 18:
+            v = E.step(a); bools.append(v)
+        elif k < 30 and bools:
+            p, q = bools[rng.below(len(bools))], bools[rng.below(len(bools))]
+            v = [E.set_and(p, q), E.set_or(p, q), E.mul(p, q), E.set_inv(p), E.set_xor(p, q), E.neg(p)][rng.below(6)]
+            if v.tag != E.NEG:
+                bools.append(v)
+        elif k < 45:
+            v = E.add(a, b)
+        elif k < 60:
+            v = E.mul(a, b)
+        elif k < 68:
+            v = E.max(a, b)
+        elif k < 76:
+            v = E.min(a, b)
+        elif k < 82:
+            v = E.neg(a)
+        elif k < 87:
+            v = E.abs(a)
+        elif k < 92:
+            v = E.recip(a)
+        elif k < 96:
+            v = E.sqrt(E.abs(a))
+        else:
+            v = E.sub(E.nat(1), a)                      # 1 - a with a NOT necessarily boolean
+        pool.append(v)
+    chans = []
+    for c in range(3):
+        acc = pool[-1 - c]
+        for _ in range(6):
+            acc = E.add(acc, E.mul(pool[rng.below(len(pool))], E.nat(rng.between(1, 9))))
+        chans.append(E.mul(E.min(E.max(acc, E.neg(E.nat(2))), E.nat(3)), E.nat(50)))
+    return E.to_bytes([w, h], E.share_let(chans))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_scenes_bit_exact(monkeypatch, seed):
+    """Property test of lowering + both code generators against the oracle on seeded random programs
+    (no transcendentals: every bit must match), unsegmented and cut into small segments."""
+    w, h = 24, 5
+    scene = _random_scene(seed + 100, w, h, 260)
+    for seg in ("100000", "64"):
+        monkeypatch.setenv("MARAY_JIT_SEGMENT_VALUES", seg)
+        _check_scene(scene, w, [0, 2, 4])
