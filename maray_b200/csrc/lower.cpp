@@ -396,6 +396,11 @@ void lower_job(void* arg) {
         live[i] = cand[i]->size() == dfs_order.size() ? max_live(*cand[i]) : 0xffffffffu;
         if (live[i] < live[best]) best = i;
     }
+    // tooling: MARAY_SCHEDULE=0..3 forces a candidate (order never changes a value, only live ranges)
+    if (const char* e = std::getenv("MARAY_SCHEDULE")) {
+        int k = std::atoi(e);
+        if (k >= 0 && k < 4 && live[k] != 0xffffffffu) best = k;
+    }
     const std::vector<uint32_t>& chosen = *cand[best];
     ProgramStats st;
     st.max_live = live[best];
