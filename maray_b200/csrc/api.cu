@@ -63,6 +63,7 @@ struct Gpu {
     cudaKernel_t jit_pre_x = nullptr, jit_pre_y = nullptr;
     double* d_colv = nullptr; size_t colv_cap = 0;     // hoisting tables (doubles)
     double* d_rowv = nullptr; size_t rowv_cap = 0;
+    cudaEvent_t hoist_done = nullptr;                  // last launch that read the tables (they are per GPU, not per stream)
     uint64_t* d_code = nullptr;
     uint64_t* d_code_uni = nullptr;   // row-uniform form of the bytecode (MARAY_INTERP_UNIFORM=1)
     double* d_consts = nullptr;
@@ -507,6 +508,10 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
                 CU_TRY(h, cudaMalloc(&g.d_rowv, need_r * sizeof(double)));
                 g.rowv_cap = need_r;
             }
+            // The tables are one per GPU: a band issued on another stream must not overwrite them while
+            // the previous band's kernel still reads them (maray_cuda_render_band takes any stream).
+            if (!g.hoist_done) CU_TRY(h, cudaEventCreateWithFlags(&g.hoist_done, cudaEventDisableTiming));
+            else CU_TRY(h, cudaStreamWaitEvent(stream, g.hoist_done, 0));
             const MrTexture* tex = g.d_textab;
             uint32_t base = 0;
             if (h->jit_ncol) {
@@ -524,6 +529,7 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
         void* args[] = {&p};
         unsigned grid = (n + h->jit_block - 1) / h->jit_block;
         CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, h->jit_dyn_smem, stream));
+        if (g.hoist_done && (h->jit_ncol || h->jit_nrow)) CU_TRY(h, cudaEventRecord(g.hoist_done, stream));
     } else {
         const unsigned span_uni = h->interp_block_uni * h->interp_ppt_uni;
         // blocks inside one row, and no idle lanes (an idle lane re-evaluates pixel p0, whose row may differ)
@@ -749,6 +755,7 @@ void maray_cuda_destroy(maray_cuda_t* h) {
         if (g.d_out) cudaFree(g.d_out);
         if (g.d_f64) cudaFree(g.d_f64);
         if (g.d_sink) cudaFree(g.d_sink);
+        if (g.hoist_done) cudaEventDestroy(g.hoist_done);
         if (g.ev0) cudaEventDestroy(g.ev0);
         if (g.ev1) cudaEventDestroy(g.ev1);
         if (g.stream) cudaStreamDestroy(g.stream);

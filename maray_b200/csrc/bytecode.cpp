@@ -161,13 +161,13 @@ private:
             if (acc_holds == n.a && !is_const(n.a)) { /* keep */ }
             else if (acc_holds == n.b && !is_const(n.b)) { first = n.b; second = n.a; swap = true; }
             else if (is_const(n.a)) { first = n.b; second = n.a; swap = true; }   // a constant can only be `second`
-            uint32_t tmp = NONE;
             if (is_const(first)) {
-                // both operands constant: only App reaches here (arithmetic was folded).  Put one in a slot.
+                // both operands constant: only App reaches here (arithmetic was folded).  One of them goes
+                // through the accumulator -- not through a slot: the kernel fetches the operands of the
+                // next instruction before this one stores, so a slot written here would be read stale.
                 emit(BC_MOV, BC_F_SWAP | BC_F_B_CONST, 0, 0, uint32_t(kidx[first]));
-                tmp = store_last();
                 acc_holds = NONE;
-                a = tmp;
+                flags |= BC_F_ACC_A;
             } else if (!first_fields(first, &flags, &a)) return;
             if (swap) flags |= BC_F_SWAP;
             if (!second_fields(second, &flags, &b)) return;
@@ -185,7 +185,6 @@ private:
             default: err = "internal: unexpected binary op"; return;
             }
             emit(op, flags, dst, a, b);
-            if (tmp != NONE) free_slots.push_back(tmp);
             consume(n.a);
             consume(n.b);
         }

@@ -492,9 +492,12 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
                         : "extern \"C\" __global__ void maray_pre_y(double* __restrict__ tab, const unsigned int n, const unsigned int base, const MrTexture* __restrict__ T) {\n";
             src += "  const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;\n  if (t >= n) return;\n  (void)T;\n";
             src += colk ? "  const double X = (double)(base + t);\n" : "  const double Y = (double)(base + t);\n";
+            // Values that depend on neither coordinate but are not literals either (a texture fetch at
+            // constant coordinates and what is computed from it) may feed the x-only / y-only cone: both
+            // prologues evaluate them too (there are at most a handful).
             for (uint32_t id : prog.order) {
                 const Node& n = prog.nodes[id];
-                if (n.op == OP_X || n.op == OP_Y || n.dep != (colk ? DEP_X : DEP_Y)) continue;
+                if (n.op == OP_X || n.op == OP_Y || (n.dep != (colk ? DEP_X : DEP_Y) && n.dep != DEP_CONST)) continue;
                 em_pre.statement(src, id);
                 if (load_kind[id] == which) {
                     std::snprintf(buf, sizeof buf, "  tab[%uu * n + t] = v%u;\n", table_index[id], id);

@@ -177,21 +177,27 @@ void* thunk_main(void* p) { Thunk* t = static_cast<Thunk*>(p); t->fn(t->arg); re
 
 }  // namespace
 
-void run_with_big_stack(void (*fn)(void*), void* arg) {
+bool run_with_big_stack(void (*fn)(void*), void* arg) {
     pthread_attr_t at;
     pthread_attr_init(&at);
     pthread_attr_setstacksize(&at, size_t(1) << 30);
     Thunk t{fn, arg};
     pthread_t th;
-    if (pthread_create(&th, &at, thunk_main, &t) == 0) pthread_join(th, nullptr);
-    else fn(arg);   // could not get the big stack: run on the caller's
+    // No fallback to the caller's stack: the loader accepts trees nested millions deep, which the
+    // default 8 MiB cannot survive -- failing is better than a stack overflow.
+    const bool started = pthread_create(&th, &at, thunk_main, &t) == 0;
+    if (started) pthread_join(th, nullptr);
     pthread_attr_destroy(&at);
+    return started;
 }
 
 bool parse_maray(const uint8_t* bytes, size_t len, Scene* out, std::string* err) {
     if (len < 8) { if (err) *err = "not a .maray file (shorter than the size header)"; return false; }
     ParseJob j{bytes, len, out, err, false};
-    run_with_big_stack(parse_job, &j);
+    if (!run_with_big_stack(parse_job, &j)) {
+        if (err) *err = "cannot start the parser thread (1 GiB stack unavailable)";
+        return false;
+    }
     return j.ok;
 }
 

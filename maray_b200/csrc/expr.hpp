@@ -60,7 +60,8 @@ struct Scene {
 bool parse_maray(const uint8_t* bytes, size_t len, Scene* out, std::string* err);
 
 // Runs fn(arg) on a thread with a 1 GiB (virtual) stack: scene trees can be very deep and the
-// loader/lowering are recursive.
-void run_with_big_stack(void (*fn)(void*), void* arg);
+// loader/lowering are recursive.  Returns false (fn not run) when the thread cannot be created; fn must
+// not let an exception escape.
+bool run_with_big_stack(void (*fn)(void*), void* arg);
 
 }  // namespace maray

@@ -3,6 +3,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <new>
 #include <unordered_map>
 
 #include "program.hpp"
@@ -221,8 +223,27 @@ struct LowerJob {
     bool ok;
 };
 
+void lower_job_body(LowerJob* j);
+
+// Runs on its own (big-stack) thread: nothing may escape it -- an exception that leaves a thread's
+// start routine ends the process, it never reaches the caller of run_with_big_stack.
 void lower_job(void* arg) {
     LowerJob* j = static_cast<LowerJob*>(arg);
+    try {
+        lower_job_body(j);
+    } catch (const std::bad_alloc&) {
+        *j->err = "out of memory while lowering";
+        j->ok = false;
+    } catch (const std::exception& e) {
+        *j->err = std::string("lowering failed: ") + e.what();
+        j->ok = false;
+    } catch (...) {
+        *j->err = "lowering failed";
+        j->ok = false;
+    }
+}
+
+void lower_job_body(LowerJob* j) {
     Lowering L(*j->tex);
     uint32_t roots[3];
     for (int c = 0; c < 3; c++) {
@@ -527,10 +548,8 @@ void lower_job(void* arg) {
 bool lower_scene(const Scene& scene, const std::vector<TextureDim>& textures, Program* out, std::string* err) {
     std::string local;
     LowerJob j{&scene, &textures, out, err ? err : &local, false};
-    try {
-        run_with_big_stack(lower_job, &j);
-    } catch (const std::bad_alloc&) {
-        if (err) *err = "out of memory while lowering";
+    if (!run_with_big_stack(lower_job, &j)) {
+        if (err) *err = "cannot start the lowering thread (1 GiB stack unavailable)";
         return false;
     }
     return j.ok;

@@ -2,6 +2,8 @@
 
 #include <zlib.h>
 
+#include <new>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -92,11 +94,21 @@ bool read_png_rgb8(const std::string& path, uint32_t* w_out, uint32_t* h_out, st
     // bytes per complete pixel as the filters see it (1 for sub-byte samples), bytes per row
     const size_t bpp = sub_byte ? 1 : size_t(channels) * (depth / 8);
     const size_t stride = sub_byte ? (size_t(w) * depth + 7) / 8 : size_t(w) * bpp;
-    std::vector<uint8_t> raw((stride + 1) * h);
+    // A hostile IHDR must not drive the allocations: the inflated size is bounded (1 GiB of samples, which
+    // also keeps every size below in range) and cannot exceed what deflate can expand the IDAT bytes to.
+    const uint64_t raw_bytes = (uint64_t(stride) + 1) * h;
+    if (raw_bytes > (uint64_t(1) << 30)) return fail("image too large (more than 1 GiB of samples)");
+    if (raw_bytes > uint64_t(idat.size()) * 1032 + 1024) return fail("corrupt image data (IDAT too short for the declared size)");
+    std::vector<uint8_t> raw;
+    try {
+        raw.resize(size_t(raw_bytes));
+        rgb->assign(size_t(w) * h * 3, 0);
+    } catch (const std::bad_alloc&) {
+        return fail("out of memory");
+    }
     uLongf rawlen = uLongf(raw.size());
     if (uncompress(raw.data(), &rawlen, idat.data(), uLong(idat.size())) != Z_OK || rawlen != raw.size()) return fail("corrupt image data");
     std::vector<uint8_t> prev(stride, 0), cur(stride);
-    rgb->assign(size_t(w) * h * 3, 0);
     for (uint32_t y = 0; y < h; y++) {
         const uint8_t* line = &raw[(stride + 1) * y];
         int ft = line[0];
@@ -113,7 +125,12 @@ bool read_png_rgb8(const std::string& path, uint32_t* w_out, uint32_t* h_out, st
             cur[i] = uint8_t(x);
         }
         uint8_t* dst = &(*rgb)[size_t(y) * w * 3];
-        const size_t sample = depth / 8;   // 16-bit: big-endian, keep the high byte
+        const size_t sample = depth / 8;
+        // 16-bit samples (big-endian) are reduced the way the reference's image 0.25.1 `to_rgb8()` does it
+        // (examples/maray.rs:61): round(v / 257) = (v + 128) / 257, not the high byte.
+        auto s8 = [&](const uint8_t* q) -> uint8_t {
+            return sample == 2 ? uint8_t(((unsigned(q[0]) << 8 | q[1]) + 128u) / 257u) : q[0];
+        };
         for (uint32_t xx = 0; xx < w; xx++) {
             uint8_t packed;
             const uint8_t* px = &cur[xx * bpp];
@@ -125,8 +142,8 @@ bool read_png_rgb8(const std::string& path, uint32_t* w_out, uint32_t* h_out, st
                 px = &packed;
             }
             switch (ctype) {
-            case 0: case 4: dst[3 * xx] = dst[3 * xx + 1] = dst[3 * xx + 2] = px[0]; break;
-            case 2: case 6: dst[3 * xx] = px[0]; dst[3 * xx + 1] = px[sample]; dst[3 * xx + 2] = px[2 * sample]; break;
+            case 0: case 4: dst[3 * xx] = dst[3 * xx + 1] = dst[3 * xx + 2] = s8(px); break;
+            case 2: case 6: dst[3 * xx] = s8(px); dst[3 * xx + 1] = s8(px + sample); dst[3 * xx + 2] = s8(px + 2 * sample); break;
             case 3: {
                 size_t idx = px[0];
                 if (3 * idx + 2 >= plte.size()) return fail("palette index out of range");

@@ -20,7 +20,7 @@ import numpy as np
 
 from . import expr as E
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 class Lcg:
@@ -43,8 +43,9 @@ class Lcg:
 
 # ---- config 1 -------------------------------------------------------------------------------------
 def chess_1k() -> bytes:
-    """The reference's shipped scene, byte for byte (data/chess.maray; sha256 b1ad82f4...baaba4)."""
-    with open(os.path.join(_GOLDEN, "chess.maray"), "rb") as f:
+    """The reference's shipped scene, byte for byte (data/chess.maray; sha256 b1ad82f4...baaba4): a bench
+    and test INPUT owned by the package (maray_b200/data/), not an oracle."""
+    with open(os.path.join(_DATA, "chess.maray"), "rb") as f:
         return f.read()
 
 

@@ -419,6 +419,7 @@ typedef struct {
     const Textures *tex;      /* rt.ctx */
     uint32_t n_functions;     /* rt.functions.len() */
     int fault;                /* set when the Rust code would panic (functions[id] out of range) */
+    double *probe;            /* diagnostic (mo_step_margin): smallest relative |step argument| seen, in ULP */
 } Rt;
 
 static const Ctx EMPTY_CTX = {0, NULL, NULL};
@@ -432,6 +433,7 @@ static inline double rust_min(double a, double b) { return (a != a) ? b : ((b < 
 typedef struct { double v; int depx; } ValDep;
 
 static double eval2(const Expr *e, Rt *rt, const double v[2], const Ctx *ctx, Cache *cache);
+static void probe_step(const Expr *arg, double s, Rt *rt, const double v[2], const Ctx *ctx, Cache *cache);
 static int dep_x(const Expr *e, Rt *rt, const double v[2], const Ctx *ctx, Cache *cache);
 
 /* Cache::val src/cache.rs:23-42 */
@@ -466,6 +468,7 @@ static double eval2(const Expr *e, Rt *rt, const double v[2], const Ctx *ctx, Ca
     case T_SQRT: return sqrt(eval2(e->a, rt, v, ctx, cache));
     case T_STEP: {                                                        /* :644-647 */
         double s = eval2(e->a, rt, v, ctx, cache);
+        if (rt->probe) probe_step(e->a, s, rt, v, ctx, cache);
         return (s >= 0.0) ? 1.0 : 0.0;
     }
     case T_SIN: return sin(eval2(e->a, rt, v, ctx, cache));               /* platform libm */
@@ -489,6 +492,34 @@ static double eval2(const Expr *e, Rt *rt, const double v[2], const Ctx *ctx, Ca
     }
     }
     return NAN;
+}
+
+/* Diagnostic only (tests attribute a 0<->255 difference between two renderers to a `step` whose
+ * argument is a rounding error away from zero): how far is this step's argument from
+ * zero, in units in the last place of the larger of the two terms whose sum it is?  Looks through
+ * Arc/Decor/Neg and through a Var to its definition; an argument that is not a sum is measured
+ * against itself (margin 2^52: never "close").  Not part of the restated algorithm. */
+static void probe_step(const Expr *arg, double s, Rt *rt, const double v[2], const Ctx *ctx, Cache *cache) {
+    const Expr *t = arg;
+    for (int hops = 0; hops < 64; hops++) {
+        if (t->tag == T_ARC || t->tag == T_DECOR || t->tag == T_NEG) { t = t->a; continue; }
+        if (t->tag == T_VAR) {
+            const Expr *def = NULL;
+            for (uint64_t i = 0; i < ctx->n; i++) if (ctx->ids[i] == t->n) { def = ctx->defs[i]; break; }
+            if (!def) break;
+            t = def;
+            continue;
+        }
+        break;
+    }
+    double scale = fabs(s);
+    if (t->tag == T_ADD) {
+        Rt q = *rt; q.probe = NULL;
+        double a = eval2(t->a, &q, v, ctx, cache), b = eval2(t->b, &q, v, ctx, cache);
+        scale = fmax(fabs(a), fabs(b));
+    }
+    double margin = (s != s) ? INFINITY : ((scale > 0.0) ? fabs(s) / (scale * 0x1p-52) : 0.0);
+    if (margin < *rt->probe) *rt->probe = margin;
 }
 
 static int dep_x(const Expr *e, Rt *rt, const double v[2], const Ctx *ctx, Cache *cache) {
@@ -685,7 +716,7 @@ int mo_set_textures(mo_scene *s, uint32_t n, const uint8_t *const *rgb, const ui
 typedef struct { const mo_scene *s; int ch; double x, y; double out; int fault; } EvalJob;
 static void *eval_thread(void *arg) {
     EvalJob *j = (EvalJob *)arg;
-    Rt rt = {&j->s->tex, j->s->tex.n * ALIGN, 0};
+    Rt rt = {&j->s->tex, j->s->tex.n * ALIGN, 0, NULL};
     Cache c; cache_init(&c);
     double v[2] = {j->x, j->y};
     j->out = eval2(j->s->color[j->ch], &rt, v, &EMPTY_CTX, &c);
@@ -696,6 +727,27 @@ static void *eval_thread(void *arg) {
 double mo_eval(const mo_scene *s, int channel, double x, double y) {
     EvalJob j = {s, channel, x, y, 0.0, 0}; pthread_t th;
     if (run_big_stack(eval_thread, &j, &th)) return NAN;
+    pthread_join(th, NULL);
+    return j.out;
+}
+
+/* Diagnostic: the smallest step margin (see probe_step) over all `step`s the three channels evaluate at
+ * pixel (x, y); +inf when no step is evaluated. */
+typedef struct { const mo_scene *s; double x, y; double out; } MarginJob;
+static void *margin_thread(void *arg) {
+    MarginJob *j = (MarginJob *)arg;
+    double m = INFINITY;
+    Rt rt = {&j->s->tex, j->s->tex.n * ALIGN, 0, &m};
+    Cache c; cache_init(&c);
+    double v[2] = {j->x, j->y};
+    for (int ch = 0; ch < 3; ch++) (void)eval2(j->s->color[ch], &rt, v, &EMPTY_CTX, &c);
+    cache_free(&c);
+    j->out = m;
+    return NULL;
+}
+double mo_step_margin(const mo_scene *s, double x, double y) {
+    MarginJob j = {s, x, y, 0.0}; pthread_t th;
+    if (run_big_stack(margin_thread, &j, &th)) return NAN;
     pthread_join(th, NULL);
     return j.out;
 }
@@ -724,7 +776,7 @@ typedef struct {
 static void *render_thread(void *arg) {
     RenderJob *j = (RenderJob *)arg;
     const mo_scene *s = j->s;
-    Rt rt = {&s->tex, s->tex.n * ALIGN, 0};
+    Rt rt = {&s->tex, s->tex.n * ALIGN, 0, NULL};
     Cache cache; cache_init(&cache);
     uint32_t ww = j->x1 - j->x0, hh = j->n_rows;
     size_t plane = (size_t)ww * hh;

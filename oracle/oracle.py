@@ -44,6 +44,8 @@ def lib():
         L.mo_fixed_bytes.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         L.mo_eval.restype = ctypes.c_double
         L.mo_eval.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+        L.mo_step_margin.restype = ctypes.c_double
+        L.mo_step_margin.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]
         L.mo_render_window.argtypes = [ctypes.c_void_p] + [ctypes.c_uint32] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.mo_render_rows.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32,
                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -92,6 +94,12 @@ class OracleScene:
     def eval(self, channel: int, x: float, y: float = 0.0) -> float:
         """`Expr::eval` (reference src/lib.rs:617-620) generalised to a y coordinate."""
         return float(lib().mo_eval(self._h, channel, x, y))
+
+    def step_margin(self, x: float, y: float) -> float:
+        """Diagnostic: how close the nearest `step` argument at pixel (x, y) is to zero, in ULP of the larger
+        term of the sum it comes from (inf when no step is evaluated).  Tests use it to attribute a
+        0<->255 difference to a step flip."""
+        return float(lib().mo_step_margin(self._h, x, y))
 
     def render_window(self, x0: int, x1: int, y0: int, y1: int, threads: int = 0, want_f64: bool = False):
         """RGB8 array (y1-y0, x1-x0, 3) of that window of the image; with want_f64 also the raw

@@ -25,5 +25,5 @@ def _built():
 
 @pytest.fixture(scope="session")
 def chess_bytes():
-    with open(os.path.join(GOLDEN, "chess.maray"), "rb") as f:
+    with open(os.path.join(ROOT, "maray_b200", "data", "chess.maray"), "rb") as f:
         return f.read()

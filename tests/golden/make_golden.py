@@ -1,7 +1,9 @@
 """How the fixtures in this directory were made (run by hand in the development container, where the
 reference checkout is mounted at /root/reference; nothing at test or bench time reads that path).
 
-  chess.maray            copy of /root/reference/data/chess.maray   (sha256 b1ad82f4...baaba4, legacy wire layout)
+  ../../maray_b200/data/chess.maray
+                         copy of /root/reference/data/chess.maray   (sha256 b1ad82f4...baaba4, legacy wire layout);
+                         it is an input scene of the benchmark, so the package owns it
   chess_reference.png    copy of /root/reference/images/chess.png    (decoded RGB8 sha256 b6f0efcf...2ccac2)
   chess_oracle_1024.png  the oracle's own render of chess.maray at its stored size
                          (decoded RGB8 sha256 4d2ca7dd...743bba -- the value an independent numpy evaluator
@@ -23,11 +25,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 def main() -> None:
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
-    shutil.copyfile(os.path.join(ref, "data", "chess.maray"), os.path.join(HERE, "chess.maray"))
+    scene_path = os.path.join(os.path.dirname(os.path.dirname(HERE)), "maray_b200", "data", "chess.maray")
+    shutil.copyfile(os.path.join(ref, "data", "chess.maray"), scene_path)
     shutil.copyfile(os.path.join(ref, "images", "chess.png"), os.path.join(HERE, "chess_reference.png"))
     from oracle.oracle import OracleScene
 
-    with open(os.path.join(HERE, "chess.maray"), "rb") as f:
+    with open(scene_path, "rb") as f:
         raw = f.read()
     rgb = OracleScene(raw).render()
     Image.fromarray(rgb).save(os.path.join(HERE, "chess_oracle_1024.png"))

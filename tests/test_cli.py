@@ -47,7 +47,9 @@ def test_cli_renders_textured_scene_like_the_oracle(tmp_path, backend):
             pal.save(path); arr = np.array(pal.convert("RGB"))
         else:
             g16 = (rgb[:, :, 0].astype(np.uint16) << 8) | 0x5A
-            Image.fromarray(g16).save(path); arr = np.repeat((g16 >> 8).astype(np.uint8)[:, :, None], 3, axis=2)
+            Image.fromarray(g16).save(path)
+            # image 0.25.1 `to_rgb8()` rounds 16-bit samples: (v + 128) / 257 (examples/maray.rs:61)
+            arr = np.repeat(((g16.astype(np.uint32) + 128) // 257).astype(np.uint8)[:, :, None], 3, axis=2)
         files.append(path); arrays.append(arr)
     x, y = E.x(), E.y()
     color = [E.app(E.channel(0, 0), x, y), E.add(E.app(E.channel(1, 1), x, y), E.app(E.channel(2, 2), y, x)),
@@ -65,8 +67,9 @@ def test_cli_renders_textured_scene_like_the_oracle(tmp_path, backend):
 
 def test_png_codec_reads_what_pillow_writes(tmp_path):
     """The CLI's built-in PNG codec (csrc/png.cpp) against Pillow, on the CPU: RGB, RGBA, 8/4/2/1-bit
-    palette, 8/4/2/1-bit and 16-bit grey must decode to what `convert("RGB")` gives (16-bit: the high
-    byte), and what the writer writes must read back unchanged."""
+    palette, 8/4/2/1-bit and 16-bit grey must decode to what `convert("RGB")` gives (16-bit: rounded as
+    the reference's image 0.25.1 `to_rgb8()` does, (v + 128) / 257 -- 0x01FF is 2, not 1), and what the
+    writer writes must read back unchanged.  A header that declares an absurd size is an error, not a crash."""
     csrc = os.path.join(ROOT, "maray_b200", "csrc")
     exe = str(tmp_path / "pngtool")
     (tmp_path / "pngtool.cpp").write_text(r'''
@@ -84,7 +87,7 @@ int main(int argc, char** argv) {
     rgb = scenes.synthetic_textures(1, 37)[0][:29]          # odd sizes: rows do not end on byte boundaries
     grey = rgb[:, :, 0]
     cases = {"rgb": Image.fromarray(rgb), "rgba": Image.fromarray(np.dstack([rgb, grey]), "RGBA"),
-             "grey8": Image.fromarray(grey), "grey16": Image.fromarray((grey.astype(np.uint16) << 8) | 0x5A),
+             "grey8": Image.fromarray(grey), "grey16": Image.fromarray((grey.astype(np.uint16) << 8) | 0xFF),
              "bilevel": Image.fromarray(grey > 100)}
     for colours in (256, 16, 4, 2):
         cases[f"pal{colours}"] = Image.fromarray(rgb).quantize(colours)
@@ -97,8 +100,22 @@ int main(int argc, char** argv) {
         assert r.returncode == 0, (name, r.stderr)
         got = np.frombuffer(r.stdout, np.uint8).reshape(29, 37, 3)
         if name == "grey16":
-            want = np.repeat(grey[:, :, None], 3, axis=2)
+            v16 = (grey.astype(np.uint32) << 8) | 0xFF
+            want = np.repeat(((v16 + 128) // 257).astype(np.uint8)[:, :, None], 3, axis=2)
+            assert (want[:, :, 0] != grey).any()         # rounding, not the high byte
         else:
             want = np.array(img.convert("RGB"))
         assert np.array_equal(got, want), name
         assert np.array_equal(np.array(Image.open(back).convert("RGB")), want), name
+    # hostile IHDR: 2^31 x 2^31 pixels declared over a few bytes of data
+    import struct, zlib
+    def chunk(t, d): return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+    evil = tmp_path / "evil.png"
+    evil.write_bytes(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 1 << 31, 1 << 31, 8, 2, 0, 0, 0)) +
+                     chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b""))
+    r = subprocess.run([exe, str(evil)], capture_output=True)
+    assert r.returncode == 1 and b"too large" in r.stderr
+    evil.write_bytes(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 20000, 15000, 8, 2, 0, 0, 0)) +
+                     chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b""))
+    r = subprocess.run([exe, str(evil)], capture_output=True)
+    assert r.returncode == 1 and b"corrupt" in r.stderr

@@ -52,6 +52,21 @@ def test_textured_scene_bit_exact():
     _check_scene(scenes.textured(256, 128), 256, [0, 64, 127], tex)
 
 
+def test_texture_fetch_at_constant_coordinates(monkeypatch):
+    """App(channel, const, const) -- both coordinates literal.  The bytecode must not route one of them
+    through a slot (the kernel fetches operands one instruction ahead of the store); with hoisting on, the
+    prologue kernels must define such a value when an x-only / y-only value reads it."""
+    tex = scenes.synthetic_textures(2, 16)
+    x, y = E.x(), E.y()
+    t57 = E.app(E.channel(0, 1), E.nat(5), E.nat(7))
+    color = [E.add(t57, x), E.mul(E.sin(E.add(E.app(E.channel(1, 2), E.nat(3), E.nat(2)), x)), y),
+             E.add(E.mul(t57, y), E.app(E.channel(1, 0), E.nat(15), E.nat(0)))]
+    scene = E.to_bytes([24, 6], color)
+    _check_scene(scene, 24, [0, 5], tex)
+    monkeypatch.setenv("MARAY_JIT_HOIST", "1")
+    _check_scene(scene, 24, [0, 5], tex)
+
+
 def test_deep_scene_bit_exact():
     _check_scene(scenes.deep(96, 64, n_values=600, seed=4), 96, [0, 33])
 
