@@ -7,6 +7,7 @@
 //   one device->host copy hands the frame to the caller.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <nvrtc.h>
 
@@ -333,6 +334,32 @@ void cache_store(const std::string& path, const std::vector<char>& cubin, uint32
     if (!ok) std::remove(tmp.c_str());
 }
 
+// Where finished cubins are kept.  On by default (the reference compiles per render, src/wasm.rs:136-158,
+// and NVRTC is ~1 ms per value): $MARAY_JIT_CACHE, else $XDG_CACHE_HOME/maray_b200, else ~/.cache/maray_b200.
+// MARAY_JIT_CACHE set to "", "0" or "off" turns it off.  Returns "" when there is no usable directory.
+std::string jit_cache_dir() {
+    std::string dir;
+    if (const char* e = std::getenv("MARAY_JIT_CACHE")) {
+        dir = e;
+        if (dir.empty() || dir == "0" || dir == "off") return "";
+    } else if (const char* x = std::getenv("XDG_CACHE_HOME"); x && *x) {
+        dir = std::string(x) + "/maray_b200";
+    } else if (const char* hm = std::getenv("HOME"); hm && *hm) {
+        dir = std::string(hm) + "/.cache/maray_b200";
+    } else {
+        return "";
+    }
+    // mkdir -p (the last two levels are enough for the defaults)
+    for (size_t at = dir.find('/', 1); ; at = dir.find('/', at + 1)) {
+        std::string part = at == std::string::npos ? dir : dir.substr(0, at);
+        if (!part.empty()) ::mkdir(part.c_str(), 0755);
+        if (at == std::string::npos) break;
+    }
+    struct stat sb;
+    if (::stat(dir.c_str(), &sb) != 0 || !S_ISDIR(sb.st_mode) || ::access(dir.c_str(), W_OK) != 0) return "";
+    return dir;
+}
+
 int nvrtc_compile(maray_cuda* h) {
     const size_t n_units = h->modules.size();
     const bool link = n_units > 1;
@@ -364,15 +391,14 @@ int nvrtc_compile(maray_cuda* h) {
     h->stats.link_ms = 0.0;
 
     std::string cache_path;
-    if (const char* dir = std::getenv("MARAY_JIT_CACHE")) {
-        if (*dir) {
-            cache_path = std::string(dir) + "/" + cache_key(h->modules, options) + ".mrcubin";
-            uint32_t regs = 0;
-            if (cache_load(cache_path, &h->cubin, &regs)) {
-                h->stats.jit_registers = regs;
-                h->stats.jit_cache_hit = 1;
-                return MARAY_OK;
-            }
+    const std::string cache_dir = jit_cache_dir();
+    if (!cache_dir.empty()) {
+        cache_path = cache_dir + "/" + cache_key(h->modules, options) + ".mrcubin";
+        uint32_t regs = 0;
+        if (cache_load(cache_path, &h->cubin, &regs)) {
+            h->stats.jit_registers = regs;
+            h->stats.jit_cache_hit = 1;
+            return MARAY_OK;
         }
     }
 

@@ -8,6 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# Finished cubins are kept in the tree (git-ignored, shipped to the GPU box with the snapshot), so a test
+# run does not pay NVRTC again for a scene it has compiled before (key: generated text + options + version).
+os.environ.setdefault("MARAY_JIT_CACHE", os.path.join(ROOT, ".jitcache"))
 
 
 def pytest_configure(config):
