@@ -64,7 +64,7 @@ typedef struct maray_cuda_stats {
     /* back end */
     uint32_t backend;
     uint32_t interp_instructions; /* bytecode length (interpreter back end)                          */
-    uint32_t interp_slots;        /* per-pixel value slots the bytecode needs                        */
+    uint32_t interp_slots;        /* per-pixel (wide) value slots the bytecode needs                 */
     uint32_t jit_segments;        /* device functions the generated source was cut into              */
     uint32_t jit_frame_slots;     /* per-thread frame doubles (0 when not segmented)                 */
     uint32_t jit_registers;       /* registers per thread of the generated kernel (0 = unknown)      */
@@ -73,7 +73,9 @@ typedef struct maray_cuda_stats {
     uint32_t jit_units;           /* translation units compiled (1, or 1 + segments when linked)     */
     uint32_t jit_compile_threads; /* host threads that ran NVRTC concurrently (0 on a cache hit)     */
     uint32_t jit_cache_hit;       /* 1 when the cubin came from the MARAY_JIT_CACHE directory        */
-    uint32_t interp_uniform_slots;/* per-block row-uniform slots (interpreter, MARAY_INTERP_UNIFORM=1; else 0) */
+    uint32_t interp_uniform_slots;/* per-block row-uniform scalar slots (interpreter; 0 in the all-wide form) */
+    uint32_t interp_block;        /* interpreter launch shape: threads per block ...                 */
+    uint32_t interp_pixels_per_thread; /* ... and pixels per thread (a block spans block*ppt pixels of one row) */
     /* timings, milliseconds */
     double lower_ms;              /* Expr -> SSA                                                     */
     double codegen_ms;            /* SSA -> source / bytecode                                        */

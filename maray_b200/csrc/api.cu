@@ -66,7 +66,6 @@ struct Gpu {
     double* d_rowv = nullptr; size_t rowv_cap = 0;
     cudaEvent_t hoist_done = nullptr;                  // last launch that read the tables (they are per GPU, not per stream)
     uint64_t* d_code = nullptr;
-    uint64_t* d_code_uni = nullptr;   // row-uniform form of the bytecode (MARAY_INTERP_UNIFORM=1)
     double* d_consts = nullptr;
     double* d_sink = nullptr;
     bool peer_to_0 = false;
@@ -88,12 +87,8 @@ struct maray_cuda {
     std::vector<std::string> modules;   // every translation unit of the last NVRTC compile
     std::vector<char> cubin;
     Bytecode bc;
-    unsigned interp_block = 128, interp_ppt = 2;
-    // Opt-in (MARAY_INTERP_UNIFORM=1), written after this round's GPU budget was spent -- run on no GPU yet:
-    // the row-uniform bytecode and its launch shape; used for launches whose blocks lie inside one row.
-    Bytecode bc_uni;
-    bool have_uni = false;
-    unsigned interp_block_uni = 0, interp_ppt_uni = 0;
+    std::vector<uint64_t> bc_device;                   // bc.code with operand fields scaled for the launch shape
+    unsigned interp_block = 128, interp_ppt = 2;       // launch shape: threads per block, pixels per thread
     unsigned jit_block = 256;
     unsigned jit_dyn_smem = 0;                         // dynamic shared memory of the generated kernel
     unsigned jit_maxreg = 0;
@@ -128,7 +123,6 @@ void release_backend(maray_cuda* h) {
         if (g.d_colv) { cudaFree(g.d_colv); g.d_colv = nullptr; g.colv_cap = 0; }
         if (g.d_rowv) { cudaFree(g.d_rowv); g.d_rowv = nullptr; g.rowv_cap = 0; }
         if (g.d_code) { cudaFree(g.d_code); g.d_code = nullptr; }
-        if (g.d_code_uni) { cudaFree(g.d_code_uni); g.d_code_uni = nullptr; }
         if (g.d_consts) { cudaFree(g.d_consts); g.d_consts = nullptr; }
     }
     h->compiled = false;
@@ -487,26 +481,33 @@ int nvrtc_compile(maray_cuda* h) {
     return MARAY_OK;
 }
 
-// Interpreter launch shape: as many resident warps as the slot file allows.
+// Interpreter launch shape.  The per-thread slot file (n_wide * P * 8 bytes) bounds how many warps an SM
+// holds; the loop wants ~8 warp-pixels per scheduler in flight (W warps x P pixels: one bytecode
+// instruction is a chain of dependent shared-memory and FP64 latencies) and a larger P amortises the
+// decode, so: score = min(W * P, 8) + P / 4, W = resident warps per scheduler (measured sweep: profiles/).
 void choose_interp_shape(maray_cuda* h) {
-    const size_t budget = 200 * 1024;   // leave room under the 227 KiB per-block limit
+    const unsigned n_scal = unsigned(h->bc.consts.size()) + h->bc.n_uniform;
+    auto fits = [&](unsigned b, unsigned p) { return interp_smem_bytes(b, p, h->bc.n_wide, n_scal) <= 227 * 1024; };
     if (const char* e = std::getenv("MARAY_INTERP_SHAPE")) {   // "block,pixels_per_thread" (tuning)
         unsigned b = 0, p = 0;
-        if (std::sscanf(e, "%u,%u", &b, &p) == 2 && b % 32 == 0 && (p == 1 || p == 2 || p == 4) &&
-            interp_smem_bytes(b, p, h->bc.n_slots, unsigned(h->bc.consts.size())) <= 227 * 1024) {
+        if (std::sscanf(e, "%u,%u", &b, &p) == 2 && b % 32 == 0 && b >= 32 && b <= 512 && (p == 1 || p == 2 || p == 4) && fits(b, p)) {
             h->interp_block = b; h->interp_ppt = p;
             return;
         }
     }
-    // more resident warps beat more pixels per thread (measured: 256x1 is 15-30 % faster than 128x2)
-    const unsigned shapes[][2] = {{256, 2}, {256, 1}, {128, 1}, {64, 1}, {32, 1}};
-    for (auto& sh : shapes) {
-        if (interp_smem_bytes(sh[0], sh[1], h->bc.n_slots, unsigned(h->bc.consts.size())) <= budget) {
-            h->interp_block = sh[0]; h->interp_ppt = sh[1];
-            return;
-        }
-    }
     h->interp_block = 0;   // does not fit
+    double best = -1.0;
+    const unsigned blocks[] = {256, 128, 64};
+    const unsigned ppts[] = {4, 2, 1};
+    for (unsigned p : ppts)
+        for (unsigned b : blocks) {
+            if (!fits(b, p)) continue;
+            const size_t per_block = interp_smem_bytes(b, p, h->bc.n_wide, n_scal) + 1024;   // + the per-block reservation
+            unsigned resident = unsigned(std::min<size_t>(size_t(228) * 1024 / per_block, std::min<size_t>(32, 2048 / b)));
+            const double warps_per_scheduler = double(resident) * b / 32.0 / 4.0;
+            const double score = std::min(warps_per_scheduler * p, 8.0) + p / 4.0 + (b == 128 ? 0.01 : 0.0);
+            if (score > best) { best = score; h->interp_block = b; h->interp_ppt = p; }
+        }
 }
 
 int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint8_t* d_out, double* d_f64,
@@ -557,14 +558,26 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
         CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, h->jit_dyn_smem, stream));
         if (g.hoist_done && (h->jit_ncol || h->jit_nrow)) CU_TRY(h, cudaEventRecord(g.hoist_done, stream));
     } else {
-        const unsigned span_uni = h->interp_block_uni * h->interp_ppt_uni;
-        // blocks inside one row, and no idle lanes (an idle lane re-evaluates pixel p0, whose row may differ)
-        if (h->have_uni && g.d_code_uni && span_uni && w % span_uni == 0 && p0 % span_uni == 0 && n % span_uni == 0) {
-            CU_TRY(h, launch_interp(p, g.d_code_uni, unsigned(h->bc_uni.code.size()), g.d_consts, unsigned(h->bc_uni.consts.size()),
-                                    h->bc_uni.n_slots, h->interp_block_uni, h->interp_ppt_uni, stream, h->bc_uni.n_uniform, true));
-        } else {
-            CU_TRY(h, launch_interp(p, g.d_code, unsigned(h->bc.code.size()), g.d_consts, unsigned(h->bc.consts.size()),
-                                    h->bc.n_slots, h->interp_block, h->interp_ppt, stream));
+        // The interpreter renders windows [x0,x1) x rows with every block inside one row: a linear pixel range
+        // is at most a partial first row, whole rows, and a partial last row.
+        uint32_t left = n, pix = p0;
+        size_t done = 0;
+        while (left) {
+            const uint32_t y = pix / w, x = pix - y * w;
+            uint32_t cols, rows;
+            if (x != 0 || left < w) { cols = std::min(left, w - x); rows = 1; }
+            else { cols = w; rows = left / w; }
+            MrTileParams t;
+            t.out = d_out + 3 * done;
+            t.f64_out = d_f64 ? d_f64 + done : nullptr;
+            t.f64_plane = f64_plane;
+            t.tex = g.d_textab;
+            t.x0 = x; t.x1 = x + cols; t.y0 = y; t.rows = rows; t.nxb = 0;
+            t.out_aligned = (reinterpret_cast<uintptr_t>(t.out) % 16 == 0) ? 1u : 0u;
+            CU_TRY(h, launch_interp(t, g.d_code, unsigned(h->bc.code.size()), g.d_consts, unsigned(h->bc.consts.size()),
+                                    h->bc.n_uniform, h->bc.n_wide, !h->bc.row_uniform, h->interp_block, h->interp_ppt, stream));
+            const uint32_t count = cols * rows;
+            done += count; pix += count; left -= count;
         }
     }
     return MARAY_OK;
@@ -904,33 +917,25 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         if (rc) return rc;
         h->stats.jit_cubin_bytes = uint32_t(h->cubin.size());
     } else {
-        if (!compile_bytecode(h->prog, &h->bc, &err)) return fail(h, MARAY_E_COMPILE, err);
-        if (h->bc.code.size() & 1) h->bc.code.push_back(bc_encode(BC_END, 0, 0, 0, 0));   // 16-byte cp.async granules
+        // Row-uniform form by default; the all-wide form when the scalar file would crowd out the slot file
+        // (or MARAY_INTERP_UNIFORM=0, for A/B).
+        bool uniform = true;
+        if (const char* e = std::getenv("MARAY_INTERP_UNIFORM")) uniform = std::strtoul(e, nullptr, 10) != 0;
+        if (!compile_bytecode(h->prog, &h->bc, &err, uniform)) return fail(h, MARAY_E_COMPILE, err);
+        if (uniform && h->bc.n_uniform > 4096 && !compile_bytecode(h->prog, &h->bc, &err, false)) return fail(h, MARAY_E_COMPILE, err);
+        if (h->bc.code.size() & 1) h->bc.code.push_back(bc_encode(BC_H_END, 0, 0, 0, 0));   // 16-byte cp.async granules
         choose_interp_shape(h);
         if (!h->interp_block)
-            return fail(h, MARAY_E_UNSUPPORTED, "program needs " + std::to_string(h->bc.n_slots) +
+            return fail(h, MARAY_E_UNSUPPORTED, "program needs " + std::to_string(h->bc.n_wide) +
                                                     " live values per pixel, more than the interpreter's shared-memory slot file holds");
-        h->have_uni = false;
-        h->stats.interp_uniform_slots = 0;
-        if (const char* e = std::getenv("MARAY_INTERP_UNIFORM")) {
-            if (std::strtoul(e, nullptr, 10) != 0) {
-                if (!compile_bytecode(h->prog, &h->bc_uni, &err, true)) return fail(h, MARAY_E_COMPILE, err);
-                if (h->bc_uni.code.size() & 1) h->bc_uni.code.push_back(bc_encode(BC_END, 0, 0, 0, 0));
-                // same constants in the same order as the per-pixel form: the device copy is shared
-                const unsigned shapes[][2] = {{256, 2}, {256, 1}, {128, 1}, {64, 1}, {32, 1}};
-                h->interp_block_uni = 0;
-                for (auto& sh : shapes)
-                    if (interp_smem_bytes(sh[0], sh[1], h->bc_uni.n_slots, unsigned(h->bc_uni.consts.size()), h->bc_uni.n_uniform) <= 200 * 1024) {
-                        h->interp_block_uni = sh[0]; h->interp_ppt_uni = sh[1];
-                        break;
-                    }
-                h->have_uni = h->interp_block_uni != 0 && h->bc_uni.consts == h->bc.consts;
-                if (h->have_uni) h->stats.interp_uniform_slots = h->bc_uni.n_uniform;
-            }
-        }
+        h->bc_device = bytecode_for_launch(h->bc, h->interp_block * h->interp_ppt / 2, &err);
+        if (h->bc_device.empty()) return fail(h, MARAY_E_UNSUPPORTED, err);
         h->stats.codegen_ms = now_ms() - t1;
         h->stats.interp_instructions = uint32_t(h->bc.code.size());
-        h->stats.interp_slots = h->have_uni ? h->bc_uni.n_slots : h->bc.n_slots;
+        h->stats.interp_slots = h->bc.n_wide;
+        h->stats.interp_uniform_slots = h->bc.n_uniform;
+        h->stats.interp_block = h->interp_block;
+        h->stats.interp_pixels_per_thread = h->interp_ppt;
     }
     h->backend = backend;
 
@@ -952,12 +957,8 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
                     CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_y, g.lib, kJitPreYName));
                 }
             } else {
-                CU_TRY(h, cudaMalloc(&g.d_code, h->bc.code.size() * sizeof(uint64_t)));
-                CU_TRY(h, cudaMemcpy(g.d_code, h->bc.code.data(), h->bc.code.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
-                if (h->have_uni) {
-                    CU_TRY(h, cudaMalloc(&g.d_code_uni, h->bc_uni.code.size() * sizeof(uint64_t)));
-                    CU_TRY(h, cudaMemcpy(g.d_code_uni, h->bc_uni.code.data(), h->bc_uni.code.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
-                }
+                CU_TRY(h, cudaMalloc(&g.d_code, h->bc_device.size() * sizeof(uint64_t)));
+                CU_TRY(h, cudaMemcpy(g.d_code, h->bc_device.data(), h->bc_device.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
                 CU_TRY(h, cudaMalloc(&g.d_consts, h->bc.consts.size() * sizeof(double)));
                 CU_TRY(h, cudaMemcpy(g.d_consts, h->bc.consts.data(), h->bc.consts.size() * sizeof(double), cudaMemcpyHostToDevice));
             }
@@ -1054,7 +1055,7 @@ int maray_cuda_get_source(const maray_cuda_t* h, char* buf, size_t cap, size_t* 
 int maray_cuda_get_bytecode(const maray_cuda_t* h, uint64_t* code, size_t cap_instr, size_t* n_instr, double* consts,
                             size_t cap_consts, size_t* n_consts) {
     if (!h) return MARAY_E_INVALID;
-    const Bytecode& bc = h->have_uni ? h->bc_uni : h->bc;   // with MARAY_INTERP_UNIFORM=1: the row-uniform form
+    const Bytecode& bc = h->bc;
     if (n_instr) *n_instr = bc.code.size();
     if (n_consts) *n_consts = bc.consts.size();
     if (code) std::memcpy(code, bc.code.data(), std::min(cap_instr, bc.code.size()) * sizeof(uint64_t));

@@ -1,24 +1,34 @@
-// Bytecode of the interpreter back end: a flat, single-pass register program with one accumulator
-// per pixel and numbered value slots (version 2).
+// Bytecode of the interpreter back end (version 3): a flat, single-pass program with TWO accumulators
+// and two slot files, laid out for a launch in which every block lies inside one image row.
 //
-// Why this shape: the per-pixel slots live in shared memory, and shared-memory capacity and latency
-// -- not the FP64 pipe -- bound the interpreter.  Every instruction is
+// Why this shape.  A block of B threads renders B*P consecutive pixels of ONE row, so a value that does
+// not depend on x ("row-uniform": everything made of y and constants -- the reference keeps exactly these
+// across a row in its Cache, reference src/cache.rs:18-20 + Expr::dep_x src/lib.rs:675-706) is one number
+// per block.  Such values are computed once per thread as a SCALAR (one FP64 instruction per warp instead
+// of P) and live in a small per-block scalar file next to the constants; values that depend on x are
+// WIDE (P per thread) and live in the per-thread slot file, which is what bounds occupancy.  On the
+// shipped chess scene this takes the per-pixel slot file from 86 to ~30 values.
 //
-//      acc = op(first, second);   if (ST) slot[dst] = acc
+// Every instruction is
 //
-// where `first` is the accumulator (ACC_A) or slot[a] and `second` is slot[b], constant[b] (B_CONST)
-// or the accumulator (FWD_B: b is the slot the previous instruction just stored).  Keeping chains in
-// the accumulator saves slot traffic; naming both operands lets the kernel fetch the NEXT
-// instruction's operands while the current one executes (the loop is latency-bound otherwise).
+//      acc  = op(first, second);   [wide[dst] = acc]       (wide shape:   P values per thread)
+//      sacc = op(first, second);   [scal[dst] = sacc]      (scalar shape: 1 value per block)
+//
+// and each operand is one of four kinds:
+//      A  the wide accumulator            W  wide slot (per pixel)
+//      T  the scalar accumulator          S  scalar file entry (constant pool, then row-uniform slots)
+// A scalar instruction reads T/S only.  There are no operand-order tricks: f64::max/min and App are not
+// symmetric (NaN, +-0, x/y), so both operands can be of any kind and keep the scene's order.
 //
 // Instruction word (64 bit):
-//   bits  0.. 7  opcode (BcOp)
-//   bits  8..15  flags (BC_F_*)
-//   bits 16..31  dst slot (BC_TEX: texture*4 + channel instead; TEX never stores)
-//   bits 32..47  a: slot index of the first operand (ignored with ACC_A)
-//   bits 48..63  b: slot or constant index of the second operand
-// SWAP evaluates op(second, first) -- f64::max/min and App are not symmetric (NaN / +-0 / x,y).
-// Slot 0 holds X and slot 1 holds Y (`x as f64`, `y as f64`) when the program starts.
+//   bits  0.. 7  handler id (BcHandler): shape, operation and -- for the hot wide operations -- both
+//                operand kinds, so the kernel's dispatch is ONE indexed jump into a specialised body
+//   bits  8..15  flags: BC_F_STORE, and the operand kinds again (read by the generic bodies)
+//   bits 16..31  dst slot (wide or scalar file by shape).  TEX: texture*4 + channel (TEX never stores)
+//   bits 32..47  a: wide slot / scalar index of the first operand (ignored for A/T)
+//   bits 48..63  b: same for the second operand
+// Wide slot 0 holds X (`x as f64`) and scalar entry n_consts holds Y when the program starts
+// (row-uniform form); in the all-wide form (row_uniform = false) wide slot 1 holds Y.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -28,42 +38,63 @@
 
 namespace maray {
 
+enum BcKind : uint8_t { BC_K_A = 0, BC_K_W = 1, BC_K_S = 2, BC_K_T = 3 };
+
 enum BcOp : uint8_t {
     BC_END = 0,
-    BC_MOV,                                            // acc = first (or second with SWAP)
+    BC_MOV,                                            // acc = first
     BC_ADD, BC_MUL, BC_MAX, BC_MIN,                    // acc = first op second
     BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,   // acc = f(first)
     BC_TEX,                                            // acc = texture(dst field)(x = first, y = second)
-    BC_OUT_R, BC_OUT_G, BC_OUT_B,                      // channel value = first
+    BC_OUT_R, BC_OUT_G, BC_OUT_B,                      // channel value = first (accumulators unchanged)
     BC_COUNT
 };
 
-constexpr uint32_t BC_F_STORE = 1u;      // slot[dst] = acc after the operation
-constexpr uint32_t BC_F_ACC_A = 2u;      // first operand is the accumulator
-constexpr uint32_t BC_F_SWAP = 4u;       // compute op(second, first)
-constexpr uint32_t BC_F_B_CONST = 8u;    // second operand is constant[b]
-constexpr uint32_t BC_F_FWD_B = 16u;     // second operand is the accumulator (slot b was stored by the previous instruction)
-// Row-uniform slots (optional form, compile_bytecode(.., row_uniform = true)): a value that depends on y
-// only is the same for every pixel of a row, so when every block of a launch lies inside one row it
-// needs ONE word per block, not one per thread.  Uniform slots are numbered separately and never
-// recycled: every warp computes and stores every such value itself (same bits), so a warp only ever
-// reads what it has written and no barrier is needed.
-constexpr uint32_t BC_F_A_UNI = 32u;     // first operand is uniform slot a
-constexpr uint32_t BC_F_B_UNI = 64u;     // second operand is uniform slot b
-constexpr uint32_t BC_F_ST_UNI = 128u;   // the store (BC_F_STORE) goes to uniform slot dst
+// Handler ids.  Wide operations with both kinds in the id (specialised bodies):
+//   binary  ADD/MUL/MAX/MIN : BC_H_BIN + (op - BC_ADD) * 16 + ka * 4 + kb
+//   unary   NEG..LN, MOV    : BC_H_UN  + u * 4 + ka          (u = op - BC_NEG; MOV is u = 8)
+//   OUT_R/G/B               : BC_H_OUT + c * 4 + ka
+// Generic bodies (kinds from the flags): BC_H_TEX (wide), BC_H_SCALAR + op (scalar shape, any op).
+constexpr uint32_t BC_H_END = 0;
+constexpr uint32_t BC_H_BIN = 16;                      // 16 .. 79
+constexpr uint32_t BC_H_UN = 80;                       // 80 .. 115
+constexpr uint32_t BC_H_OUT = 116;                     // 116 .. 127
+constexpr uint32_t BC_H_TEX = 128;
+constexpr uint32_t BC_H_SCALAR = 144;                  // 144 + BcOp
+constexpr uint32_t BC_H_COUNT = BC_H_SCALAR + BC_COUNT;
+
+constexpr uint32_t BC_F_STORE = 1u;                    // store the result to slot dst of the shape's file
+constexpr uint32_t BC_F_KA_SHIFT = 2, BC_F_KB_SHIFT = 4;   // operand kinds (BcKind), two bits each
 
 struct Bytecode {
-    std::vector<uint64_t> code;      // ends with BC_END
-    std::vector<double> consts;
-    uint32_t n_slots = 2;            // per-pixel slots, including X and Y
-    uint32_t n_uniform = 0;          // per-block slots (row-uniform form only)
+    std::vector<uint64_t> code;      // ends with BC_H_END
+    std::vector<double> consts;      // scalar file entries 0 .. consts.size()-1
+    uint32_t n_wide = 1;             // wide slots, including X (and Y in the all-wide form)
+    uint32_t n_uniform = 0;          // row-uniform scalar slots, including Y (0 in the all-wide form)
+    bool row_uniform = true;
 };
 
-inline uint64_t bc_encode(BcOp op, uint32_t flags, uint32_t dst, uint32_t a, uint32_t b) {
-    return uint64_t(op) | (uint64_t(flags & 0xff) << 8) | (uint64_t(dst & 0xffff) << 16) | (uint64_t(a & 0xffff) << 32) |
-           (uint64_t(b & 0xffff) << 48);
+inline uint64_t bc_encode(uint32_t handler, uint32_t flags, uint32_t dst, uint32_t a, uint32_t b) {
+    return uint64_t(handler & 0xff) | (uint64_t(flags & 0xff) << 8) | (uint64_t(dst & 0xffff) << 16) |
+           (uint64_t(a & 0xffff) << 32) | (uint64_t(b & 0xffff) << 48);
+}
+inline uint32_t bc_handler(BcOp op, bool scalar_shape, uint32_t ka, uint32_t kb) {
+    if (op == BC_END) return BC_H_END;
+    if (scalar_shape) return BC_H_SCALAR + op;
+    if (op >= BC_ADD && op <= BC_MIN) return BC_H_BIN + (op - BC_ADD) * 16 + ka * 4 + kb;
+    if (op >= BC_NEG && op <= BC_LN) return BC_H_UN + (op - BC_NEG) * 4 + ka;
+    if (op == BC_MOV) return BC_H_UN + 8 * 4 + ka;
+    if (op >= BC_OUT_R && op <= BC_OUT_B) return BC_H_OUT + (op - BC_OUT_R) * 4 + ka;
+    return BC_H_TEX;
 }
 
-bool compile_bytecode(const Program& prog, Bytecode* out, std::string* err, bool row_uniform = false);
+// row_uniform = false compiles the all-wide form (every value per pixel; used when a program has more
+// row-uniform values than the scalar file holds).
+bool compile_bytecode(const Program& prog, Bytecode* out, std::string* err, bool row_uniform = true);
+
+// The program as the kernel reads it for one launch shape: every wide slot index (operands of kind W and
+// the dst of a storing wide instruction) multiplied by slot16 = P * B / 2, the size of one wide slot in
+// 16-byte units, so that an operand address is one shift-add.  Empty + err when a field would overflow.
+std::vector<uint64_t> bytecode_for_launch(const Bytecode& bc, uint32_t slot16, std::string* err);
 
 }  // namespace maray

@@ -1,5 +1,5 @@
 // Hand-written sm_100a kernels of the render path:
-//   maray_interp<P>   -- the bytecode interpreter (MARAY_BACKEND_INTERP)
+//   maray_interp<P>   -- the bytecode interpreter (MARAY_BACKEND_INTERP), P pixels per thread
 //   fp64_issue_rate   -- FP64-pipe issue-rate microbenchmark (the roofline denominator)
 // The NVRTC back end's kernel is generated at run time (codegen.cpp) from the same device_sem.cuh.
 //
@@ -15,22 +15,25 @@
 namespace maray {
 
 // ------------------------------------------------------------------------------------------------
-// Bytecode interpreter (bytecode.hpp, version 2).
+// Bytecode interpreter (bytecode.hpp, version 3).
 //
-// Mapping: one thread evaluates P pixels (P independent dependency chains); a block of B threads
-// covers B*P consecutive pixels of the linear image index.  Per-pixel value slots live in shared
-// memory as slots[slot][k][tid] (consecutive threads hit consecutive 8-byte words: conflict-free),
-// the constant pool is copied to shared memory once per block (read as a broadcast).  The
-// instruction stream is warp-uniform: it is staged from global memory into shared memory in
-// double-buffered chunks with cp.async and every warp reads the same word (a broadcast), so there is
-// no divergence anywhere in the loop.
+// Mapping: a block of B threads renders B*P consecutive pixels of ONE image row (thread t: columns
+// xs + k*B + t, k < P); the grid is (blocks per row) x (rows).  Values that depend on x are WIDE: P per
+// thread, in registers while they are the accumulator, otherwise in the per-thread slot file in shared
+// memory (16-byte words per thread for P >= 2, so one LDS.128 moves two pixels and a warp's accesses are
+// conflict-free).  Values that do not depend on x are SCALARS: one per block, kept with the constants
+// in a small scalar file every lane reads as a broadcast, computed with one FP64 instruction per warp.
+// Every warp computes and stores every scalar itself (same bits), and scalar slots are never recycled,
+// so a warp only ever reads what it wrote: no barrier.  The instruction stream is warp-uniform: staged
+// from global memory in double-buffered chunks with cp.async, every lane reads the same word.
 //
-// The loop is software-pipelined: while instruction i executes, instruction i+1 is fetched and BOTH
-// of its operands are loaded (speculatively -- flags decide later which of them are used).  The one
-// read-after-write case this cannot see, an operand stored by instruction i itself, is marked by the
-// host compiler (ACC_A / FWD_B: take the accumulator instead).
+// Dispatch: the handler id in the low byte selects, with ONE indexed branch, a body specialised on the
+// operation AND on where both operands come from (accumulator / slot / scalar file / scalar
+// accumulator), so a body is just its loads, P FP64 instructions and nothing else; the store (a flag)
+// follows the switch.  Rare forms (texture fetch, everything in the scalar shape) take generic bodies
+// that read the operand kinds from the flags.
 
-constexpr int kChunk = 512;   // instructions per staged chunk (4 KiB)
+constexpr int kChunk = 256;   // instructions per staged chunk (2 KiB)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned int s = (unsigned int)__cvta_generic_to_shared(smem);
@@ -39,44 +42,159 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// (Measured and rejected: moving sqrt/1/x/sin/exp/ln/texture bodies out of line to shrink the loop --
-// chess_1k 37.3 vs 40.6 ms, but the transcendental-heavy deep scene 28.9 vs 23.5 ms.)
-//
-// U = true is the row-uniform form of the bytecode (bytecode.hpp, BC_F_*_UNI): values that depend on y
-// only live in n_uniform per-BLOCK words placed after the constants; every block of such a launch lies
-// inside one image row (the host checks it).  Every warp computes and stores every uniform value itself
-// with identical bits and uniform slots are never recycled, so no barrier is needed.  With U = false
-// none of that code exists in the kernel.
-template <int P, bool U>
-__global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code, unsigned int n_instr,
-                             const double* __restrict__ consts, unsigned int n_consts, unsigned int n_slots,
-                             unsigned int n_uniform) {
+// The per-thread view of the two files.  Wide slot operands arrive PRE-SCALED by the host (the launch
+// shape is fixed when the program is uploaded): field = slot * (P * B) / 2, the slot's offset in 16-byte
+// units (P * B is even for every shape), so an address is one shift-add.
+template <int P>
+struct Files {
+    unsigned char* wide;        // this thread's first byte of wide slot 0
+    unsigned int half_stride;   // P == 4: bytes between the two 16-byte halves of a slot (16 * B)
+    const double* scal;         // scalar file (constants, then row-uniform slots)
+
+    __device__ __forceinline__ void load(unsigned int s16, double (&v)[P]) const {
+        const unsigned char* q = wide + ((size_t)s16 << 4);
+        if constexpr (P == 1) {
+            v[0] = *reinterpret_cast<const double*>(q);
+        } else {
+#pragma unroll
+            for (int hlf = 0; hlf < P / 2; hlf++) {
+                const double2 t = *reinterpret_cast<const double2*>(q + hlf * half_stride);
+                v[2 * hlf] = t.x; v[2 * hlf + 1] = t.y;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(unsigned int s16, const double (&v)[P]) const {
+        unsigned char* q = wide + ((size_t)s16 << 4);
+        if constexpr (P == 1) {
+            *reinterpret_cast<double*>(q) = v[0];
+        } else {
+#pragma unroll
+            for (int hlf = 0; hlf < P / 2; hlf++)
+                *reinterpret_cast<double2*>(q + hlf * half_stride) = make_double2(v[2 * hlf], v[2 * hlf + 1]);
+        }
+    }
+};
+
+template <int P, int K>
+__device__ __forceinline__ void mr_fetch(const Files<P>& f, const double (&acc)[P], double sacc, unsigned int idx, double (&v)[P]) {
+    if constexpr (K == BC_K_A) {
+#pragma unroll
+        for (int k = 0; k < P; k++) v[k] = acc[k];
+    } else if constexpr (K == BC_K_W) {
+        f.load(idx, v);
+    } else if constexpr (K == BC_K_S) {
+        const double s = f.scal[idx];
+#pragma unroll
+        for (int k = 0; k < P; k++) v[k] = s;
+    } else {
+#pragma unroll
+        for (int k = 0; k < P; k++) v[k] = sacc;
+    }
+}
+template <int P>
+__device__ __forceinline__ void mr_fetch_rt(const Files<P>& f, const double (&acc)[P], double sacc, unsigned int kind, unsigned int idx,
+                                            double (&v)[P]) {
+    switch (kind) {
+    case BC_K_A: mr_fetch<P, BC_K_A>(f, acc, sacc, idx, v); break;
+    case BC_K_W: mr_fetch<P, BC_K_W>(f, acc, sacc, idx, v); break;
+    case BC_K_S: mr_fetch<P, BC_K_S>(f, acc, sacc, idx, v); break;
+    default: mr_fetch<P, BC_K_T>(f, acc, sacc, idx, v); break;
+    }
+}
+
+struct OpAdd { static __device__ __forceinline__ double f(double x, double y) { return x + y; } };
+struct OpMul { static __device__ __forceinline__ double f(double x, double y) { return x * y; } };
+struct OpMax { static __device__ __forceinline__ double f(double x, double y) { return mr_max(x, y); } };
+struct OpMin { static __device__ __forceinline__ double f(double x, double y) { return mr_min(x, y); } };
+struct OpMov { static __device__ __forceinline__ double f(double x) { return x; } };
+struct OpNeg { static __device__ __forceinline__ double f(double x) { return -x; } };
+struct OpAbs { static __device__ __forceinline__ double f(double x) { return fabs(x); } };
+struct OpRecip { static __device__ __forceinline__ double f(double x) { return mr_recip(x); } };
+struct OpSqrt { static __device__ __forceinline__ double f(double x) { return mr_sqrt(x); } };
+struct OpStep { static __device__ __forceinline__ double f(double x) { return mr_step(x); } };
+struct OpSin { static __device__ __forceinline__ double f(double x) { return mr_sin(x); } };
+struct OpExp { static __device__ __forceinline__ double f(double x) { return mr_exp(x); } };
+struct OpLn { static __device__ __forceinline__ double f(double x) { return mr_log(x); } };
+
+template <int P, int KA, int KB, class Op>
+__device__ __forceinline__ void mr_bin(const Files<P>& f, double (&acc)[P], double sacc, unsigned int a, unsigned int b) {
+    double x[P], y[P];
+    mr_fetch<P, KA>(f, acc, sacc, a, x);
+    mr_fetch<P, KB>(f, acc, sacc, b, y);
+#pragma unroll
+    for (int k = 0; k < P; k++) acc[k] = Op::f(x[k], y[k]);
+}
+template <int P, int KA, class Op>
+__device__ __forceinline__ void mr_un(const Files<P>& f, double (&acc)[P], double sacc, unsigned int a) {
+    double x[P];
+    mr_fetch<P, KA>(f, acc, sacc, a, x);
+    if constexpr (KA == BC_K_S || KA == BC_K_T) {
+        const double r = Op::f(x[0]);       // a scalar operand: one evaluation serves the P pixels
+#pragma unroll
+        for (int k = 0; k < P; k++) acc[k] = r;
+    } else {
+#pragma unroll
+        for (int k = 0; k < P; k++) acc[k] = Op::f(x[k]);
+    }
+}
+
+#define MR_BIN_ROW(OPI, OP, KA)                                                                              \
+    case BC_H_BIN + (OPI) * 16 + (KA) * 4 + 0: mr_bin<P, KA, 0, OP>(F, acc, sacc, a, b); break;              \
+    case BC_H_BIN + (OPI) * 16 + (KA) * 4 + 1: mr_bin<P, KA, 1, OP>(F, acc, sacc, a, b); break;              \
+    case BC_H_BIN + (OPI) * 16 + (KA) * 4 + 2: mr_bin<P, KA, 2, OP>(F, acc, sacc, a, b); break;              \
+    case BC_H_BIN + (OPI) * 16 + (KA) * 4 + 3: mr_bin<P, KA, 3, OP>(F, acc, sacc, a, b); break;
+#define MR_BIN_CASES(OPI, OP) MR_BIN_ROW(OPI, OP, 0) MR_BIN_ROW(OPI, OP, 1) MR_BIN_ROW(OPI, OP, 2) MR_BIN_ROW(OPI, OP, 3)
+#define MR_UN_CASES(U, OP)                                                                                   \
+    case BC_H_UN + (U) * 4 + 0: mr_un<P, 0, OP>(F, acc, sacc, a); break;                                      \
+    case BC_H_UN + (U) * 4 + 1: mr_un<P, 1, OP>(F, acc, sacc, a); break;                                      \
+    case BC_H_UN + (U) * 4 + 2: mr_un<P, 2, OP>(F, acc, sacc, a); break;                                      \
+    case BC_H_UN + (U) * 4 + 3: mr_un<P, 3, OP>(F, acc, sacc, a); break;
+#define MR_OUT_CASES(C)                                                                                      \
+    case BC_H_OUT + (C) * 4 + 0: { double x[P]; mr_fetch<P, 0>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break; \
+    case BC_H_OUT + (C) * 4 + 1: { double x[P]; mr_fetch<P, 1>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break; \
+    case BC_H_OUT + (C) * 4 + 2: { double x[P]; mr_fetch<P, 2>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break; \
+    case BC_H_OUT + (C) * 4 + 3: { double x[P]; mr_fetch<P, 3>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break;
+
+template <int P>
+__global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const uint64_t* __restrict__ code, unsigned int n_instr,
+                                                    const double* __restrict__ consts, unsigned int n_consts, unsigned int n_scal,
+                                                    unsigned int n_wide, unsigned int all_wide) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [2][kChunk] instruction words | staging tile (3*B*P bytes, 16-aligned) | constants | uniform slots | slots
+    // layout: [2][kChunk] instruction words | staging tile (3*B*P bytes, 16-aligned) | scalar file | wide slots (+3 channel slots)
     uint64_t* code_s = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned char* stage = smem_raw + 2 * kChunk * sizeof(uint64_t);
     const unsigned int B = blockDim.x;
     const unsigned int tid = threadIdx.x;
-    double* consts_s = reinterpret_cast<double*>(stage + ((3u * B * P + 15u) & ~15u));
-    double* uslots = consts_s + ((n_consts + 1u) & ~1u);
-    double* slots = uslots + (U ? ((n_uniform + 1u) & ~1u) : 0u);
+    double* scal = reinterpret_cast<double*>(stage + ((3u * B * P + 15u) & ~15u));
+    double* wide = scal + ((n_scal + 1u) & ~1u);
 
-    const unsigned int first = blockIdx.x * B * P;
-    double acc[P], va[P], vb[P];
-    // channel values go to three extra slots (n_slots .. n_slots+2): keeping them in registers makes the
-    // compiler copy them at every handler join
-    double* outs = slots + (size_t)n_slots * P * B + tid;
+    Files<P> F;
+    F.wide = reinterpret_cast<unsigned char*>(wide + (P == 1 ? tid : 2u * tid));
+    F.half_stride = 16u * B;
+    F.scal = scal;
+    const unsigned int slot16 = P * B / 2u;              // one wide slot in 16-byte units
+    const unsigned int out16 = n_wide * slot16;          // the three channel slots follow the program's slots
+
+    const unsigned int row = blockIdx.x / p.nxb;
+    const unsigned int xb = blockIdx.x - row * p.nxb;
+    const unsigned int yi = p.y0 + row;
+    const unsigned int xs = p.x0 + xb * B * P;          // first column of this block
+    double acc[P];
+    double sacc = 0.0;
+    {
+        double xv[P], yv[P];
 #pragma unroll
-    for (int k = 0; k < P; k++) {
-        unsigned int j = first + k * B + tid;
-        unsigned int pix = p.p0 + (j < p.n ? j : 0u);   // idle lanes redo pixel p0
-        unsigned int yi = pix / p.W;
-        unsigned int xi = pix - yi * p.W;
-        slots[(0 * P + k) * B + tid] = (double)xi;      // `x as f64`, reference src/render.rs:25
-        slots[(1 * P + k) * B + tid] = (double)yi;
-        acc[k] = 0.0; va[k] = 0.0; vb[k] = 0.0;
+        for (int k = 0; k < P; k++) {
+            const unsigned int xi = xs + k * B + tid;
+            xv[k] = (double)(xi < p.x1 ? xi : p.x1 - 1u);   // idle lanes redo the row's last pixel; `x as f64`, reference src/render.rs:25
+            yv[k] = (double)yi;
+            acc[k] = 0.0;
+        }
+        F.store(0, xv);
+        if (all_wide) F.store(slot16, yv);
     }
-    for (unsigned int i = tid; i < n_consts; i += B) consts_s[i] = consts[i];
+    for (unsigned int i = tid; i < n_consts; i += B) scal[i] = consts[i];
+    if (!all_wide && tid == 0) scal[n_consts] = (double)yi;
 
     const unsigned int n_chunks = (n_instr + kChunk - 1) / kChunk;
     for (unsigned int i = tid; i < kChunk / 2; i += B) {   // prefetch chunk 0
@@ -85,24 +203,9 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
     }
     cp_async_commit();
 
-    // operand fetch for one instruction word
-    auto fetch = [&](uint64_t w, double* fa, double* fb) {
-        const unsigned int a = (unsigned int)(w >> 32) & 0xffffu, b = (unsigned int)(w >> 48);
-        const bool bk = (w >> 8) & BC_F_B_CONST;
-        const double* pa = slots + (size_t)a * P * B + tid;
-        const double* pb = bk ? consts_s + b : slots + (size_t)b * P * B + tid;
-        unsigned int sa = B, sb = bk ? 0u : B;
-        if constexpr (U) {
-            if ((w >> 8) & BC_F_A_UNI) { pa = uslots + a; sa = 0u; }
-            if ((w >> 8) & BC_F_B_UNI) { pb = uslots + b; sb = 0u; }
-        }
-#pragma unroll
-        for (int k = 0; k < P; k++) { fa[k] = pa[k * sa]; fb[k] = pb[k * sb]; }
-    };
-
     for (unsigned int c = 0; c < n_chunks; c++) {
         cp_async_wait_all();
-        __syncthreads();   // chunk c (and, first time, the constants and X/Y slots) landed; chunk c-1 is done
+        __syncthreads();   // chunk c (and, first time, the scalar file and X/Y) landed; chunk c-1 is done
         if (c + 1 < n_chunks) {
             uint64_t* dst = code_s + ((c + 1) & 1) * kChunk;
             const uint64_t* src = code + (size_t)(c + 1) * kChunk;
@@ -115,122 +218,102 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
         }
         const uint64_t* cs = code_s + (c & 1) * kChunk;
         const unsigned int cnt = (n_instr - c * kChunk < (unsigned)kChunk) ? (n_instr - c * kChunk) : (unsigned)kChunk;
-        uint64_t w = cs[0];
-        fetch(w, va, vb);                                  // the chunk's first instruction: not overlapped
-#pragma unroll 2
+        // (Reading one word past the chunk's last instruction is harmless: the word after buffer 0 is buffer
+        // 1's first, the word after buffer 1 is the staging tile -- both inside this block's shared memory.)
+        const uint64_t* pc = cs;
+        uint64_t wn = *pc;
         for (unsigned int i = 0; i < cnt; i++) {
-            // ---- stage 1: next instruction's word and operands (overlaps stage 2) -----------------
-            const uint64_t wn = cs[i + 1 < cnt ? i + 1 : i];
-            double na[P], nb[P];
-            fetch(wn, na, nb);
-            // ---- stage 2: execute the current instruction -------------------------------------------
-            const unsigned int lo = (unsigned int)w;
-            const unsigned int op = lo & 0xffu, fl = (lo >> 8) & 0xffu;
-            double x[P], y[P];
-#pragma unroll
-            for (int k = 0; k < P; k++) {
-                const double f = (fl & BC_F_ACC_A) ? acc[k] : va[k];
-                const double s = (fl & BC_F_FWD_B) ? acc[k] : vb[k];
-                x[k] = (fl & BC_F_SWAP) ? s : f;
-                y[k] = (fl & BC_F_SWAP) ? f : s;
-            }
-            if (op == BC_MUL) {
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = x[k] * y[k];
-            } else if (op == BC_ADD) {
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = x[k] + y[k];
-            } else if (op == BC_MOV) {
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = x[k];
-            } else if (op == BC_STEP) {
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_step(x[k]);
-            } else if (op == BC_NEG) {
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = -x[k];
-            } else if (op == BC_MIN) {
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_min(x[k], y[k]);
-            } else if (op == BC_MAX) {
-#pragma unroll
-                for (int k = 0; k < P; k++) acc[k] = mr_max(x[k], y[k]);
-            } else {
-                switch (op) {
-                case BC_ABS:
-#pragma unroll
-                    for (int k = 0; k < P; k++) acc[k] = fabs(x[k]);
-                    break;
-                case BC_RECIP:
-#pragma unroll
-                    for (int k = 0; k < P; k++) acc[k] = mr_recip(x[k]);
-                    break;
-                case BC_SQRT:
-#pragma unroll
-                    for (int k = 0; k < P; k++) acc[k] = mr_sqrt(x[k]);
-                    break;
-                case BC_SIN:
-#pragma unroll
-                    for (int k = 0; k < P; k++) acc[k] = mr_sin(x[k]);
-                    break;
-                case BC_EXP:
-#pragma unroll
-                    for (int k = 0; k < P; k++) acc[k] = mr_exp(x[k]);
-                    break;
-                case BC_LN:
-#pragma unroll
-                    for (int k = 0; k < P; k++) acc[k] = mr_log(x[k]);
-                    break;
-                case BC_TEX: {
+            const uint64_t w = wn;
+            wn = *++pc;                                    // next word: its latency hides behind this instruction
+            const unsigned int lo = (unsigned int)w, hi = (unsigned int)(w >> 32);
+            const unsigned int h = lo & 0xffu;
+            const unsigned int a = hi & 0xffffu, b = hi >> 16;   // pre-scaled by the host: see Files
+            if (h < BC_H_SCALAR) {
+                switch (h) {
+                    MR_BIN_CASES(0, OpAdd)
+                    MR_BIN_CASES(1, OpMul)
+                    MR_BIN_CASES(2, OpMax)
+                    MR_BIN_CASES(3, OpMin)
+                    MR_UN_CASES(0, OpNeg)
+                    MR_UN_CASES(1, OpAbs)
+                    MR_UN_CASES(2, OpRecip)
+                    MR_UN_CASES(3, OpSqrt)
+                    MR_UN_CASES(4, OpStep)
+                    MR_UN_CASES(5, OpSin)
+                    MR_UN_CASES(6, OpExp)
+                    MR_UN_CASES(7, OpLn)
+                    MR_UN_CASES(8, OpMov)
+                    MR_OUT_CASES(0)
+                    MR_OUT_CASES(1)
+                    MR_OUT_CASES(2)
+                case BC_H_TEX: {
+                    double x[P], y[P];
+                    mr_fetch_rt<P>(F, acc, sacc, (lo >> (8 + BC_F_KA_SHIFT)) & 3u, a, x);
+                    mr_fetch_rt<P>(F, acc, sacc, (lo >> (8 + BC_F_KB_SHIFT)) & 3u, b, y);
                     const unsigned int imm = lo >> 16;
                     const MrTexture t = p.tex[imm >> 2];
 #pragma unroll
                     for (int k = 0; k < P; k++) acc[k] = mr_tex(t.data, t.w, t.h, imm & 3u, x[k], y[k]);
                 } break;
-                case BC_OUT_R: case BC_OUT_G: case BC_OUT_B:
-#pragma unroll
-                    for (int k = 0; k < P; k++) outs[((op - BC_OUT_R) * P + k) * B] = x[k];
-                    break;
-                default: break;   // BC_END
+                default: break;   // BC_H_END
                 }
-            }
-            if (fl & BC_F_STORE) {
-                bool uni = false;
-                if constexpr (U) uni = (fl & BC_F_ST_UNI) != 0;
-                if (uni) {
-                    uslots[lo >> 16] = acc[0];       // the same bits in every thread and for every k: one row
-                } else {
-                    double* dp = slots + (size_t)(lo >> 16) * P * B + tid;
-#pragma unroll
-                    for (int k = 0; k < P; k++) dp[k * B] = acc[k];
+                if (lo & (BC_F_STORE << 8)) F.store(lo >> 16, acc);
+            } else {
+                // scalar shape: one value per block, operands from the scalar file or the scalar accumulator
+                const double x = ((lo >> (8 + BC_F_KA_SHIFT)) & 3u) == BC_K_T ? sacc : scal[a];
+                const double y = ((lo >> (8 + BC_F_KB_SHIFT)) & 3u) == BC_K_T ? sacc : scal[b];
+                switch (h - BC_H_SCALAR) {
+                case BC_MOV: sacc = x; break;
+                case BC_ADD: sacc = x + y; break;
+                case BC_MUL: sacc = x * y; break;
+                case BC_MAX: sacc = mr_max(x, y); break;
+                case BC_MIN: sacc = mr_min(x, y); break;
+                case BC_NEG: sacc = -x; break;
+                case BC_ABS: sacc = fabs(x); break;
+                case BC_RECIP: sacc = mr_recip(x); break;
+                case BC_SQRT: sacc = mr_sqrt(x); break;
+                case BC_STEP: sacc = mr_step(x); break;
+                case BC_SIN: sacc = mr_sin(x); break;
+                case BC_EXP: sacc = mr_exp(x); break;
+                case BC_LN: sacc = mr_log(x); break;
+                case BC_TEX: {
+                    const unsigned int imm = lo >> 16;
+                    const MrTexture t = p.tex[imm >> 2];
+                    sacc = mr_tex(t.data, t.w, t.h, imm & 3u, x, y);
+                } break;
+                default: break;
                 }
+                if ((lo & (BC_F_STORE << 8)) && (h - BC_H_SCALAR) != BC_TEX) scal[lo >> 16] = sacc;   // same bits from every lane
             }
-            w = wn;
-#pragma unroll
-            for (int k = 0; k < P; k++) { va[k] = na[k]; vb[k] = nb[k]; }
         }
     }
 
     // `as u8` + RGB pack through the staging tile, then coalesced 16-byte stores.
+    const unsigned int ww = p.x1 - p.x0;
+    const size_t row_first = (size_t)row * ww + (xs - p.x0);     // index of this block's first pixel in the output
+    {
+        double o_r[P], o_g[P], o_b[P];
+        F.load(out16, o_r);
+        F.load(out16 + slot16, o_g);
+        F.load(out16 + 2u * slot16, o_b);
 #pragma unroll
-    for (int k = 0; k < P; k++) {
-        unsigned int l = k * B + tid;   // pixel within the block
-        const double o_r = outs[(0 * P + k) * B], o_g = outs[(1 * P + k) * B], o_b = outs[(2 * P + k) * B];
-        stage[3u * l + 0u] = (unsigned char)mr_as_u8(o_r);
-        stage[3u * l + 1u] = (unsigned char)mr_as_u8(o_g);
-        stage[3u * l + 2u] = (unsigned char)mr_as_u8(o_b);
-        unsigned int j = first + l;
-        if (p.f64_out != nullptr && j < p.n) {
-            p.f64_out[j] = o_r;
-            p.f64_out[(size_t)p.f64_plane + j] = o_g;
-            p.f64_out[2u * (size_t)p.f64_plane + j] = o_b;
+        for (int k = 0; k < P; k++) {
+            const unsigned int l = k * B + tid;                  // pixel within the block
+            stage[3u * l + 0u] = (unsigned char)mr_as_u8(o_r[k]);
+            stage[3u * l + 1u] = (unsigned char)mr_as_u8(o_g[k]);
+            stage[3u * l + 2u] = (unsigned char)mr_as_u8(o_b[k]);
+            if (p.f64_out != nullptr && xs + l < p.x1) {
+                p.f64_out[row_first + l] = o_r[k];
+                p.f64_out[(size_t)p.f64_plane + row_first + l] = o_g[k];
+                p.f64_out[2u * (size_t)p.f64_plane + row_first + l] = o_b[k];
+            }
         }
     }
     __syncthreads();
     const unsigned int span = B * P;
-    const unsigned int valid = (p.n - first < span) ? (p.n - first) : span;
-    unsigned char* dst = p.out + 3u * (size_t)first;
-    if (p.out_aligned && valid == span && (span & 15u) == 0u) {
+    const unsigned int valid = (p.x1 - xs < span) ? (p.x1 - xs) : span;
+    unsigned char* dst = p.out + 3u * row_first;
+    if (p.out_aligned && valid == span && (span & 15u) == 0u && ((3u * row_first) & 15u) == 0u) {
         for (unsigned int i = tid; i < 3u * span / 16u; i += B)
             reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(stage)[i];
     } else {
@@ -238,45 +321,36 @@ __global__ void maray_interp(const MrParams p, const uint64_t* __restrict__ code
     }
 }
 
-size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_slots, unsigned int n_consts,
-                         unsigned int n_uniform) {
+size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_wide, unsigned int n_scal) {
     size_t stage = (3u * (size_t)block * pixels_per_thread + 15u) & ~size_t(15);
-    return 2 * kChunk * sizeof(uint64_t) + stage + (size_t)((n_consts + 1u) & ~1u) * sizeof(double) +
-           (size_t)((n_uniform + 1u) & ~1u) * sizeof(double) +
-           (size_t)(n_slots + 3u) * pixels_per_thread * block * sizeof(double);   // + 3 channel-output slots
+    return 2 * kChunk * sizeof(uint64_t) + stage + (size_t)((n_scal + 1u) & ~1u) * sizeof(double) +
+           (size_t)(n_wide + 3u) * pixels_per_thread * block * sizeof(double);   // + 3 channel-output slots
 }
 
-template <int P, bool U>
-static cudaError_t launch_interp_as(const MrParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
-                                    unsigned int n_consts, unsigned int n_slots, unsigned int n_uniform, unsigned int block,
-                                    unsigned int grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(maray_interp<P, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int P>
+static cudaError_t launch_interp_as(const MrTileParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
+                                    unsigned int n_consts, unsigned int n_scal, unsigned int n_wide, bool all_wide,
+                                    unsigned int block, unsigned int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(maray_interp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    maray_interp<P, U><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform);
+    maray_interp<P><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide ? 1u : 0u);
     return cudaGetLastError();
 }
 
-cudaError_t launch_interp(const MrParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
-                          unsigned int n_consts, unsigned int n_slots, unsigned int block, unsigned int pixels_per_thread,
-                          cudaStream_t stream, unsigned int n_uniform, bool row_uniform) {
-    if (p.n == 0) return cudaSuccess;
-    size_t smem = interp_smem_bytes(block, pixels_per_thread, n_slots, n_consts, row_uniform ? n_uniform : 0u);
-    unsigned int span = block * pixels_per_thread;
-    unsigned int grid = (p.n + span - 1) / span;
-    if (row_uniform) {
-        // every block must lie inside one image row, and there must be no idle lanes (they redo pixel p0)
-        if (p.W % span != 0 || p.p0 % span != 0 || p.n % span != 0) return cudaErrorInvalidValue;
-        switch (pixels_per_thread) {
-        case 1: return launch_interp_as<1, true>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform, block, grid, smem, stream);
-        case 2: return launch_interp_as<2, true>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform, block, grid, smem, stream);
-        case 4: return launch_interp_as<4, true>(p, d_code, n_instr, d_consts, n_consts, n_slots, n_uniform, block, grid, smem, stream);
-        default: return cudaErrorInvalidValue;
-        }
-    }
+cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
+                          unsigned int n_consts, unsigned int n_uniform, unsigned int n_wide, bool all_wide, unsigned int block,
+                          unsigned int pixels_per_thread, cudaStream_t stream) {
+    if (p.rows == 0 || p.x1 <= p.x0) return cudaSuccess;
+    const unsigned int n_scal = n_consts + n_uniform;
+    const size_t smem = interp_smem_bytes(block, pixels_per_thread, n_wide, n_scal);
+    const unsigned int span = block * pixels_per_thread;
+    p.nxb = (p.x1 - p.x0 + span - 1) / span;
+    if ((uint64_t)p.nxb * p.rows > 0x7fffffffull) return cudaErrorInvalidValue;
+    const unsigned int grid = p.nxb * p.rows;
     switch (pixels_per_thread) {
-    case 1: return launch_interp_as<1, false>(p, d_code, n_instr, d_consts, n_consts, n_slots, 0u, block, grid, smem, stream);
-    case 2: return launch_interp_as<2, false>(p, d_code, n_instr, d_consts, n_consts, n_slots, 0u, block, grid, smem, stream);
-    case 4: return launch_interp_as<4, false>(p, d_code, n_instr, d_consts, n_consts, n_slots, 0u, block, grid, smem, stream);
+    case 1: return launch_interp_as<1>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream);
+    case 2: return launch_interp_as<2>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream);
+    case 4: return launch_interp_as<4>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream);
     default: return cudaErrorInvalidValue;
     }
 }

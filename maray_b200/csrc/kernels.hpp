@@ -5,20 +5,31 @@
 #include <cstddef>
 #include <cstdint>
 
-struct MrParams;
+struct MrTexture;
+
+// One launch of the interpreter kernel renders the window [x0, x1) x [y0, y0 + rows) of the image; pixel
+// (x, y) goes to out[3 * ((y - y0) * (x1 - x0) + (x - x0))] (for whole rows of a frame: the RgbImage
+// order of reference src/render.rs:19-31) and, optionally, its raw channel values to three f64 planes
+// at the same pixel index.  Every block lies inside one row.
+struct MrTileParams {
+    unsigned char* out;
+    double* f64_out;               // optional (parity checks); plane c starts at f64_out + c * f64_plane
+    unsigned long long f64_plane;
+    const MrTexture* tex;          // device texture table (may be null when the program has no App)
+    unsigned int x0, x1, y0, rows;
+    unsigned int nxb;              // blocks per row (set by launch_interp)
+    unsigned int out_aligned;      // out is 16-byte aligned: full, aligned blocks store uint4
+};
 
 namespace maray {
 
-// Dynamic shared memory the interpreter needs for a launch configuration.
-size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_slots, unsigned int n_consts,
-                         unsigned int n_uniform = 0);
+// Dynamic shared memory the interpreter needs for a launch configuration (n_scal = constants + row-uniform slots).
+size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_wide, unsigned int n_scal);
 
 // d_code must be padded to an even number of instructions (16-byte cp.async granules).
-cudaError_t launch_interp(const MrParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
-                          unsigned int n_consts, unsigned int n_slots, unsigned int block, unsigned int pixels_per_thread,
-                          cudaStream_t stream, unsigned int n_uniform = 0, bool row_uniform = false);
-// row_uniform: the bytecode is the row-uniform form (bytecode.hpp); fails with cudaErrorInvalidValue unless
-// every block of the launch lies inside one image row and is full (W, p0 and n multiples of block * pixels_per_thread).
+cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
+                          unsigned int n_consts, unsigned int n_uniform, unsigned int n_wide, bool all_wide, unsigned int block,
+                          unsigned int pixels_per_thread, cudaStream_t stream);
 
 cudaError_t launch_fp64_issue_rate(bool fma, double* d_sink, int iters, int blocks, cudaStream_t stream);
 

@@ -123,11 +123,43 @@ def host_jit_run(source: str, w: int, p0: int, n: int, textures=()):
     return rgb, planes
 
 
-# ---- bytecode (csrc/bytecode.hpp, version 2) -------------------------------------------------------
+# ---- bytecode (csrc/bytecode.hpp, version 3) -------------------------------------------------------
 (BC_END, BC_MOV, BC_ADD, BC_MUL, BC_MAX, BC_MIN, BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,
  BC_TEX, BC_OUT_R, BC_OUT_G, BC_OUT_B) = range(18)
-F_STORE, F_ACC_A, F_SWAP, F_B_CONST, F_FWD_B = 1, 2, 4, 8, 16
-F_A_UNI, F_B_UNI, F_ST_UNI = 32, 64, 128
+K_A, K_W, K_S, K_T = 0, 1, 2, 3
+H_END, H_BIN, H_UN, H_OUT, H_TEX, H_SCALAR = 0, 16, 80, 116, 128, 144
+F_STORE, F_KA_SHIFT, F_KB_SHIFT = 1, 2, 4
+
+
+def bc_decode(w):
+    """(shape_is_scalar, op, ka, kb, store, dst, a, b) of one instruction word; checks that the handler id
+    and the flags agree on the operand kinds (the kernel's specialised bodies read the id, its generic
+    bodies the flags)."""
+    w = int(w)
+    h, fl, dst, a, b = w & 0xFF, (w >> 8) & 0xFF, (w >> 16) & 0xFFFF, (w >> 32) & 0xFFFF, (w >> 48) & 0xFFFF
+    ka, kb = (fl >> F_KA_SHIFT) & 3, (fl >> F_KB_SHIFT) & 3
+    store = bool(fl & F_STORE)
+    if h == H_END:
+        return False, BC_END, 0, 0, False, 0, 0, 0
+    if h >= H_SCALAR:
+        op = h - H_SCALAR
+        assert BC_MOV <= op <= BC_TEX and ka in (K_S, K_T), "scalar instruction with a wide operand"
+        assert kb in (K_S, K_T) or not (BC_ADD <= op <= BC_MIN or op == BC_TEX)
+        return True, op, ka, kb, store, dst, a, b
+    if H_BIN <= h < H_UN:
+        op = BC_ADD + (h - H_BIN) // 16
+        assert ((h - H_BIN) % 16) == ka * 4 + kb, "handler id and flags disagree on the operand kinds"
+    elif H_UN <= h < H_OUT:
+        u = (h - H_UN) // 4
+        op = BC_MOV if u == 8 else BC_NEG + u
+        assert (h - H_UN) % 4 == ka
+    elif H_OUT <= h < H_TEX:
+        op = BC_OUT_R + (h - H_OUT) // 4
+        assert (h - H_OUT) % 4 == ka
+    else:
+        assert h == H_TEX, f"bad handler id {h}"
+        op = BC_TEX
+    return False, op, ka, kb, store, dst, a, b
 
 
 def _vec(fn):
@@ -175,72 +207,76 @@ def tex_fetch(tex, ch, x, y):
     return out
 
 
-def bytecode_run(code, consts, xs, ys, textures=()):
-    """Executes the bytecode for the pixels (xs[i], ys[i]) the way the kernel does, INCLUDING its
-    one-instruction-ahead operand fetch: operands of instruction i+1 are read before instruction i
-    stores, so a program that forgot an ACC_A / FWD_B mark computes a wrong value here too.
-    Returns planes float64 (3, n)."""
+def bytecode_run(code, consts, xs, ys, textures=(), row_uniform=True):
+    """Executes the bytecode for the pixels (xs[i], ys[i]) the way the kernel does: a wide accumulator and
+    wide slots (one value per pixel), a scalar accumulator and the scalar file (constants, then row-uniform
+    slots; ONE value for all pixels, which must therefore share one y).  Every scalar result is computed
+    from pixel 0 and asserted to be what every other pixel would have computed -- a value wrongly classified
+    as row-uniform fails here -- and row-uniform slots are never recycled.  Returns planes float64 (3, n)."""
     xs = np.asarray(xs, dtype=np.float64)
     ys = np.asarray(ys, dtype=np.float64)
     n = xs.shape[0]
-    slots = {0: xs, 1: ys}
-    # Row-uniform form (bytecode.hpp BC_F_*_UNI): one word per BLOCK.  The kernel's blocks lie inside one
-    # row, so the pixels given here must share one y; the uniform word is read from / written by pixel 0
-    # and asserted to be the same for every pixel -- a value wrongly classified as row-uniform fails here.
-    uslots = {}
-    zero = np.zeros(n)
+    consts = np.asarray(consts, dtype=np.float64)
+    nk = consts.shape[0]
+    wide = {0: xs}
+    scal = {i: float(consts[i]) for i in range(nk)}
+    if row_uniform:
+        assert np.unique(ys).size == 1, "row-uniform bytecode must be run one row at a time"
+        scal[nk] = float(ys[0])
+    else:
+        wide[1] = ys
     acc = np.zeros(n)
+    sacc = 0.0
     out = np.zeros((3, n))
 
-    def fetch(w):
-        fl, a, b = (w >> 8) & 0xFF, (w >> 32) & 0xFFFF, (w >> 48) & 0xFFFF
-        fa = np.full(n, uslots.get(a, 0.0)) if fl & F_A_UNI else slots.get(a, zero)
-        if fl & F_B_CONST:
-            fb = np.full(n, consts[b])
-        else:
-            fb = np.full(n, uslots.get(b, 0.0)) if fl & F_B_UNI else slots.get(b, zero)
-        return fa, fb
+    def wide_operand(kind, idx):
+        if kind == K_A: return acc
+        if kind == K_W: return wide[idx]
+        if kind == K_S: return np.full(n, scal[idx])
+        return np.full(n, sacc)
 
-    words = [int(w) for w in code]
-    va, vb = fetch(words[0])
+    def apply(op, x, y, dst):
+        if op == BC_MOV: return x
+        if op == BC_ADD: return x + y
+        if op == BC_MUL: return x * y
+        if op == BC_MAX: return sem_max(x, y)
+        if op == BC_MIN: return sem_min(x, y)
+        if op == BC_NEG: return -x
+        if op == BC_ABS: return np.abs(x)
+        if op == BC_RECIP: return 1.0 / x
+        if op == BC_SQRT: return np.sqrt(x)
+        if op == BC_STEP: return np.where(x >= 0.0, 1.0, 0.0)
+        if op == BC_SIN: return _sin(x)
+        if op == BC_EXP: return _exp(x)
+        if op == BC_LN: return _log(x)
+        if op == BC_TEX: return tex_fetch(textures[dst >> 2], dst & 3, x, y)
+        raise ValueError(f"bad opcode {op}")
+
     with np.errstate(all="ignore"):
-        for i, w in enumerate(words):
-            nxt = fetch(words[i + 1]) if i + 1 < len(words) else (zero, zero)     # before this instruction's store
-            op, fl, dst = w & 0xFF, (w >> 8) & 0xFF, (w >> 16) & 0xFFFF
+        for w in code:
+            is_scalar, op, ka, kb, store, dst, a, b = bc_decode(w)
             if op == BC_END:
                 break
-            f = acc if fl & F_ACC_A else va
-            s = acc if fl & F_FWD_B else vb
-            x, y = (s, f) if fl & F_SWAP else (f, s)
-            if op == BC_MOV: acc = x
-            elif op == BC_ADD: acc = x + y
-            elif op == BC_MUL: acc = x * y
-            elif op == BC_MAX: acc = sem_max(x, y)
-            elif op == BC_MIN: acc = sem_min(x, y)
-            elif op == BC_NEG: acc = -x
-            elif op == BC_ABS: acc = np.abs(x)
-            elif op == BC_RECIP: acc = 1.0 / x
-            elif op == BC_SQRT: acc = np.sqrt(x)
-            elif op == BC_STEP: acc = np.where(x >= 0.0, 1.0, 0.0)
-            elif op == BC_SIN: acc = _sin(x)
-            elif op == BC_EXP: acc = _exp(x)
-            elif op == BC_LN: acc = _log(x)
-            elif op == BC_TEX: acc = tex_fetch(textures[dst >> 2], dst & 3, x, y)
-            elif op == BC_OUT_R: out[0] = x
-            elif op == BC_OUT_G: out[1] = x
-            elif op == BC_OUT_B: out[2] = x
-            else:
-                raise ValueError(f"bad opcode {op}")
-            if fl & F_STORE:
+            if is_scalar:
+                assert row_uniform
+                x = np.array([sacc if ka == K_T else scal[a]])
+                y = np.array([sacc if kb == K_T else scal[b]]) if (BC_ADD <= op <= BC_MIN or op == BC_TEX) else x
+                sacc = float(apply(op, x, y, dst)[0])
+                if store:
+                    assert op != BC_TEX, "TEX keeps its texture id in the dst field and must not store"
+                    assert dst >= nk and dst not in scal, "row-uniform slots are never recycled"
+                    scal[dst] = sacc
+                continue
+            x = wide_operand(ka, a)
+            if BC_OUT_R <= op <= BC_OUT_B:
+                out[op - BC_OUT_R] = x
+                assert not store
+                continue
+            y = wide_operand(kb, b) if (BC_ADD <= op <= BC_MIN or op == BC_TEX) else x
+            acc = apply(op, x, y, dst)
+            if store:
                 assert op != BC_TEX, "TEX keeps its texture id in the dst field and must not store"
-                if fl & F_ST_UNI:
-                    assert np.unique(ys).size == 1, "row-uniform bytecode must be run one row at a time"
-                    assert bits_equal(acc, np.full(n, acc[0])).all(), "a row-uniform slot got a value that varies along the row"
-                    assert dst not in uslots, "row-uniform slots are never recycled"
-                    uslots[dst] = float(acc[0])
-                else:
-                    slots[dst] = acc
-            va, vb = nxt
+                wide[dst] = acc
     return out
 
 

@@ -129,15 +129,21 @@ def test_boolean_logic_is_value_preserving(monkeypatch, chess_bytes):
                     assert np.array_equal(rgb, want_rgb.reshape(w, 3))
 
 
-def test_row_uniform_bytecode_form(monkeypatch, chess_bytes):
-    """MARAY_INTERP_UNIFORM=1 (opt-in): y-only values live in per-block words.  The bytecode must still
-    evaluate to the oracle's bits (numpy reader, one row at a time, which also checks that every
-    "row-uniform" store really is the same along the row and that uniform slots are never recycled),
+def test_row_uniform_and_all_wide_bytecode_forms(monkeypatch, chess_bytes):
+    """The bytecode's default form keeps values that do not depend on x in the per-block scalar file (the
+    GPU counterpart of the reference's row cache, src/cache.rs:18-20); MARAY_INTERP_UNIFORM=0 compiles the
+    all-wide form.  Both must evaluate to the oracle's bits (numpy reader, one row at a time, which also
+    checks that every scalar really is the same along the row and that scalar slots are never recycled),
     and the per-pixel slot file must shrink -- chess keeps 59 y-only values live at its peak."""
+    monkeypatch.setenv("MARAY_INTERP_UNIFORM", "0")
     with CudaRenderer(gpus=0) as r:
         r.load(chess_bytes)
         plain = r.compile("interp")
-    monkeypatch.setenv("MARAY_INTERP_UNIFORM", "1")
+        code0, consts0 = r.bytecode()
+    assert plain["interp_uniform_slots"] == 0 and 60 <= plain["interp_slots"] <= 100
+    _rgb, want = _oracle_window(chess_bytes, [], 0, 1024, 700, 701)
+    assert bits_equal(bytecode_run(code0, consts0, np.arange(1024), np.full(1024, 700), row_uniform=False), want.reshape(3, 1024)).all()
+    monkeypatch.delenv("MARAY_INTERP_UNIFORM")
     tex = scenes.synthetic_textures(1, 32)
     x, y = E.x(), E.y()
     mixed = E.to_bytes([40, 6], [E.add(E.mul(E.sin(E.mul(y, E.nat(3))), x), E.app(E.channel(0, 1), x, E.mul(y, E.nat(2)))),
@@ -150,10 +156,11 @@ def test_row_uniform_bytecode_form(monkeypatch, chess_bytes):
             r.load(scene)
             st = r.compile("interp")
             code, consts = r.bytecode()
-        flags = (code >> np.uint64(8)) & np.uint64(0xFF)
-        assert st["interp_uniform_slots"] > 0 and (flags & np.uint64(128)).any()
+        handlers = code & np.uint64(0xFF)
+        assert st["interp_uniform_slots"] >= 1 and (handlers >= np.uint64(144)).any()
+        assert st["interp_block"] % 32 == 0 and st["interp_pixels_per_thread"] in (1, 2, 4)
         if scene is chess_bytes:
-            assert plain["interp_slots"] == 86 and st["interp_slots"] <= 40 and plain["interp_uniform_slots"] == 0
+            assert st["interp_slots"] <= 40 and st["interp_slots"] < plain["interp_slots"] // 2
         for yrow in rows:
             _rgb, want = _oracle_window(scene, textures, 0, w, yrow, yrow + 1)
             got = bytecode_run(code, consts, np.arange(w), np.full(w, yrow), textures)
