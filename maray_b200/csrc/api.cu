@@ -89,6 +89,7 @@ struct maray_cuda {
     Bytecode bc;
     std::vector<uint64_t> bc_device;                   // bc.code with operand fields scaled for the launch shape
     unsigned interp_block = 128, interp_ppt = 2;       // launch shape: threads per block, pixels per thread
+    bool interp_tree = false;                          // MARAY_INTERP_DISPATCH=tree: C++ switch instead of the jump table (A/B)
     unsigned jit_block = 256;
     unsigned jit_dyn_smem = 0;                         // dynamic shared memory of the generated kernel
     unsigned jit_maxreg = 0;
@@ -482,12 +483,16 @@ int nvrtc_compile(maray_cuda* h) {
 }
 
 // Interpreter launch shape.  The per-thread slot file (n_wide * P * 8 bytes) bounds how many warps an SM
-// holds; the loop wants ~8 warp-pixels per scheduler in flight (W warps x P pixels: one bytecode
-// instruction is a chain of dependent shared-memory and FP64 latencies) and a larger P amortises the
-// decode, so: score = min(W * P, 8) + P / 4, W = resident warps per scheduler (measured sweep: profiles/).
+// holds, and one bytecode instruction is a chain of dependent shared-memory, branch and FP64 latencies, so
+// throughput follows the number of pixels in flight per SM: resident warps x P (measured sweeps:
+// profiles/r02_interp_sweeps.md -- at equal product P = 2 is a little ahead of P = 1 and P = 4).  Blocks
+// of any multiple of 32 threads are considered: fewer, larger blocks spend less shared memory on the
+// per-block parts (instruction chunks, scalar file, staging tile) and so hold more warps.
 void choose_interp_shape(maray_cuda* h) {
     const unsigned n_scal = unsigned(h->bc.consts.size()) + h->bc.n_uniform;
-    auto fits = [&](unsigned b, unsigned p) { return interp_smem_bytes(b, p, h->bc.n_wide, n_scal) <= 227 * 1024; };
+    auto fits = [&](unsigned b, unsigned p) {
+        return interp_smem_bytes(b, p, h->bc.n_wide, n_scal) <= 227 * 1024 && uint64_t(h->bc.n_wide + 3) * (p * b / 2) <= 0xffff;
+    };
     if (const char* e = std::getenv("MARAY_INTERP_SHAPE")) {   // "block,pixels_per_thread" (tuning)
         unsigned b = 0, p = 0;
         if (std::sscanf(e, "%u,%u", &b, &p) == 2 && b % 32 == 0 && b >= 32 && b <= 512 && (p == 1 || p == 2 || p == 4) && fits(b, p)) {
@@ -497,15 +502,17 @@ void choose_interp_shape(maray_cuda* h) {
     }
     h->interp_block = 0;   // does not fit
     double best = -1.0;
-    const unsigned blocks[] = {256, 128, 64};
-    const unsigned ppts[] = {4, 2, 1};
+    const unsigned ppts[] = {2, 4, 1};
     for (unsigned p : ppts)
-        for (unsigned b : blocks) {
+        for (unsigned b = 32; b <= 512; b += 32) {
             if (!fits(b, p)) continue;
             const size_t per_block = interp_smem_bytes(b, p, h->bc.n_wide, n_scal) + 1024;   // + the per-block reservation
-            unsigned resident = unsigned(std::min<size_t>(size_t(228) * 1024 / per_block, std::min<size_t>(32, 2048 / b)));
-            const double warps_per_scheduler = double(resident) * b / 32.0 / 4.0;
-            const double score = std::min(warps_per_scheduler * p, 8.0) + p / 4.0 + (b == 128 ? 0.01 : 0.0);
+            const unsigned resident = unsigned(std::min<size_t>(size_t(228) * 1024 / per_block, std::min<size_t>(32, 2048 / b)));
+            const double warps = double(resident) * b / 32.0;
+            // lanes past the end of a row idle: count the row width the scene was authored for
+            const unsigned span = b * p, sw = std::max<unsigned>(h->scene.size[0], 1);
+            const double row_fill = double(sw) / (double((sw + span - 1) / span) * span);
+            const double score = warps * p * (p == 2 ? 1.0 : 0.95) * row_fill - 0.001 * b;
             if (score > best) { best = score; h->interp_block = b; h->interp_ppt = p; }
         }
 }
@@ -574,8 +581,9 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
             t.tex = g.d_textab;
             t.x0 = x; t.x1 = x + cols; t.y0 = y; t.rows = rows; t.nxb = 0;
             t.out_aligned = (reinterpret_cast<uintptr_t>(t.out) % 16 == 0) ? 1u : 0u;
-            CU_TRY(h, launch_interp(t, g.d_code, unsigned(h->bc.code.size()), g.d_consts, unsigned(h->bc.consts.size()),
-                                    h->bc.n_uniform, h->bc.n_wide, !h->bc.row_uniform, h->interp_block, h->interp_ppt, stream));
+            CU_TRY(h, launch_interp(t, g.d_code, unsigned(h->bc_device.size()), g.d_consts, unsigned(h->bc.consts.size()),
+                                    h->bc.n_uniform, h->bc.n_wide, !h->bc.row_uniform, h->interp_block, h->interp_ppt, stream,
+                                    h->interp_tree));
             const uint32_t count = cols * rows;
             done += count; pix += count; left -= count;
         }
@@ -687,10 +695,12 @@ int render_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
     for (double& k : h->stats.kernel_ms) k = 0.0;
     h->stats.gather_ms = 0.0; h->stats.d2h_ms = 0.0;
 
-    const bool hoisting = h->backend == MARAY_BACKEND_NVRTC && (h->jit_ncol || h->jit_nrow);   // its tables are per launch
-    // Opt-in (MARAY_PIPELINE=1): written after this round's GPU budget was spent, so it has run on no GPU yet.
-    const char* pipe_env = std::getenv("MARAY_PIPELINE");
-    if (host_rgb && h->gpus.size() == 1 && !hoisting && pipe_env && std::strtoul(pipe_env, nullptr, 10) != 0 &&
+    // Host-bound frames of 4 MiB and more are rendered in row chunks whose device->host copies overlap the
+    // chunks still rendering (render_frame_pipelined).  Measured on chess_4k into a pageable buffer: 1 075 ->
+    // 1 245 Mpixel/s end to end (profiles/r02_calls.md).  MARAY_PIPELINE=0 turns it off (A/B).
+    bool pipelined = true;
+    if (const char* e = std::getenv("MARAY_PIPELINE")) pipelined = std::strtoul(e, nullptr, 10) != 0;
+    if (host_rgb && h->gpus.size() == 1 && pipelined &&
         (h->report_kind == MARAY_REPORT_NONE || !h->report_fn) && size_t(w) * hgt * 3 >= (size_t(4) << 20)) {
         rc = render_frame_pipelined(h, w, hgt, host_rgb);
         if (rc) return rc;
@@ -923,8 +933,8 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         if (const char* e = std::getenv("MARAY_INTERP_UNIFORM")) uniform = std::strtoul(e, nullptr, 10) != 0;
         if (!compile_bytecode(h->prog, &h->bc, &err, uniform)) return fail(h, MARAY_E_COMPILE, err);
         if (uniform && h->bc.n_uniform > 4096 && !compile_bytecode(h->prog, &h->bc, &err, false)) return fail(h, MARAY_E_COMPILE, err);
-        if (h->bc.code.size() & 1) h->bc.code.push_back(bc_encode(BC_H_END, 0, 0, 0, 0));   // 16-byte cp.async granules
         choose_interp_shape(h);
+        if (const char* e = std::getenv("MARAY_INTERP_DISPATCH")) h->interp_tree = std::string(e) == "tree";
         if (!h->interp_block)
             return fail(h, MARAY_E_UNSUPPORTED, "program needs " + std::to_string(h->bc.n_wide) +
                                                     " live values per pixel, more than the interpreter's shared-memory slot file holds");

@@ -201,21 +201,27 @@ private:
 }  // namespace
 
 std::vector<uint64_t> bytecode_for_launch(const Bytecode& bc, uint32_t slot16, std::string* err) {
-    std::vector<uint64_t> out(bc.code);
     if (uint64_t(bc.n_wide + 3) * slot16 > 0xffff) {
         if (err) *err = "slot file too large for this launch shape (16-bit operand fields)";
         return {};
     }
-    for (uint64_t& w : out) {
+    std::vector<uint64_t> out;
+    out.reserve(bc.code.size() + bc.code.size() / (kBcChunk - 1) + kBcChunk);
+    for (uint64_t w : bc.code) {
         const uint32_t h = uint32_t(w) & 0xff, fl = uint32_t(w >> 8) & 0xff;
-        if (h == BC_H_END || h >= BC_H_SCALAR) continue;
-        uint64_t dst = (w >> 16) & 0xffff, a = (w >> 32) & 0xffff, b = (w >> 48) & 0xffff;
-        if (((fl >> BC_F_KA_SHIFT) & 3u) == BC_K_W) a *= slot16;
-        const bool binary = (h >= BC_H_BIN && h < BC_H_UN) || h == BC_H_TEX;
-        if (binary && ((fl >> BC_F_KB_SHIFT) & 3u) == BC_K_W) b *= slot16;
-        if ((fl & BC_F_STORE) && h != BC_H_TEX) dst *= slot16;
-        w = (w & 0xffffull) | (dst << 16) | (a << 32) | (b << 48);
+        if (h == BC_H_END) break;                      // the padding below ends the stream
+        if (h < BC_H_SCALAR) {
+            uint64_t dst = (w >> 16) & 0xffff, a = (w >> 32) & 0xffff, b = (w >> 48) & 0xffff;
+            if (((fl >> BC_F_KA_SHIFT) & 3u) == BC_K_W) a *= slot16;
+            const bool binary = (h >= BC_H_BIN && h < BC_H_UN) || h == BC_H_TEX;
+            if (binary && ((fl >> BC_F_KB_SHIFT) & 3u) == BC_K_W) b *= slot16;
+            if ((fl & BC_F_STORE) && h != BC_H_TEX) dst *= slot16;
+            w = (w & 0xffffull) | (dst << 16) | (a << 32) | (b << 48);
+        }
+        if (out.size() % kBcChunk == kBcChunk - 1) out.push_back(bc_encode(BC_H_YIELD, 0, 0, 0, 0));
+        out.push_back(w);
     }
+    do out.push_back(bc_encode(BC_H_END, 0, 0, 0, 0)); while (out.size() % kBcChunk != 0);
     return out;
 }
 

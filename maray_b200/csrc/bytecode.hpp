@@ -54,14 +54,24 @@ enum BcOp : uint8_t {
 //   binary  ADD/MUL/MAX/MIN : BC_H_BIN + (op - BC_ADD) * 16 + ka * 4 + kb
 //   unary   NEG..LN, MOV    : BC_H_UN  + u * 4 + ka          (u = op - BC_NEG; MOV is u = 8)
 //   OUT_R/G/B               : BC_H_OUT + c * 4 + ka
-// Generic bodies (kinds from the flags): BC_H_TEX (wide), BC_H_SCALAR + op (scalar shape, any op).
+//   TEX (wide)              : BC_H_TEX   (kinds from the flags)
+// Scalar shape (operands are S or T only; t = 1 for T):
+//   binary                  : BC_H_SBIN + (op - BC_ADD) * 4 + ta * 2 + tb
+//   unary, MOV              : BC_H_SUN  + u * 2 + ta
+//   TEX                     : BC_H_STEX  (kinds from the flags)
+// The ids are dense on purpose: the kernel's dispatch is a jump table over 0 .. BC_H_COUNT-1
+// (tools/gen_interp_dispatch.py holds the same numbers).
 constexpr uint32_t BC_H_END = 0;
+constexpr uint32_t BC_H_YIELD = 1;                     // device stream only: last word of every staged chunk but the final one
 constexpr uint32_t BC_H_BIN = 16;                      // 16 .. 79
 constexpr uint32_t BC_H_UN = 80;                       // 80 .. 115
 constexpr uint32_t BC_H_OUT = 116;                     // 116 .. 127
 constexpr uint32_t BC_H_TEX = 128;
-constexpr uint32_t BC_H_SCALAR = 144;                  // 144 + BcOp
-constexpr uint32_t BC_H_COUNT = BC_H_SCALAR + BC_COUNT;
+constexpr uint32_t BC_H_SCALAR = 144;                  // first scalar-shape id
+constexpr uint32_t BC_H_SBIN = 144;                    // 144 .. 159
+constexpr uint32_t BC_H_SUN = 160;                     // 160 .. 177
+constexpr uint32_t BC_H_STEX = 178;
+constexpr uint32_t BC_H_COUNT = 179;
 
 constexpr uint32_t BC_F_STORE = 1u;                    // store the result to slot dst of the shape's file
 constexpr uint32_t BC_F_KA_SHIFT = 2, BC_F_KB_SHIFT = 4;   // operand kinds (BcKind), two bits each
@@ -80,7 +90,13 @@ inline uint64_t bc_encode(uint32_t handler, uint32_t flags, uint32_t dst, uint32
 }
 inline uint32_t bc_handler(BcOp op, bool scalar_shape, uint32_t ka, uint32_t kb) {
     if (op == BC_END) return BC_H_END;
-    if (scalar_shape) return BC_H_SCALAR + op;
+    if (scalar_shape) {
+        const uint32_t ta = ka == BC_K_T ? 1u : 0u, tb = kb == BC_K_T ? 1u : 0u;
+        if (op >= BC_ADD && op <= BC_MIN) return BC_H_SBIN + (op - BC_ADD) * 4 + ta * 2 + tb;
+        if (op >= BC_NEG && op <= BC_LN) return BC_H_SUN + (op - BC_NEG) * 2 + ta;
+        if (op == BC_MOV) return BC_H_SUN + 8 * 2 + ta;
+        return BC_H_STEX;
+    }
     if (op >= BC_ADD && op <= BC_MIN) return BC_H_BIN + (op - BC_ADD) * 16 + ka * 4 + kb;
     if (op >= BC_NEG && op <= BC_LN) return BC_H_UN + (op - BC_NEG) * 4 + ka;
     if (op == BC_MOV) return BC_H_UN + 8 * 4 + ka;
@@ -92,9 +108,14 @@ inline uint32_t bc_handler(BcOp op, bool scalar_shape, uint32_t ka, uint32_t kb)
 // row-uniform values than the scalar file holds).
 bool compile_bytecode(const Program& prog, Bytecode* out, std::string* err, bool row_uniform = true);
 
-// The program as the kernel reads it for one launch shape: every wide slot index (operands of kind W and
-// the dst of a storing wide instruction) multiplied by slot16 = P * B / 2, the size of one wide slot in
-// 16-byte units, so that an operand address is one shift-add.  Empty + err when a field would overflow.
+// The program as the kernel reads it for one launch shape:
+//  * every wide slot index (operands of kind W and the dst of a storing wide instruction) multiplied by
+//    slot16 = P * B / 2, the size of one wide slot in 16-byte units, so an operand address is one shift-add;
+//  * cut into chunks of exactly kBcChunk words, the unit the kernel stages into shared memory: every chunk
+//    but the last ends with a BC_H_YIELD word, the last is padded with BC_H_END -- the kernel's inner loop
+//    needs no bounds check, it leaves at the YIELD / END word.
+// Empty + err when a field would overflow.
+constexpr uint32_t kBcChunk = 256;
 std::vector<uint64_t> bytecode_for_launch(const Bytecode& bc, uint32_t slot16, std::string* err);
 
 }  // namespace maray

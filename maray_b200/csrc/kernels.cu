@@ -10,6 +10,7 @@
 
 #include "bytecode.hpp"
 #include "device_sem.cuh"
+#include "interp_dispatch.inc"   // generated: tools/gen_interp_dispatch.py (jump-table dispatch + hot bodies, inline PTX)
 #include "kernels.hpp"
 
 namespace maray {
@@ -33,7 +34,7 @@ namespace maray {
 // follows the switch.  Rare forms (texture fetch, everything in the scalar shape) take generic bodies
 // that read the operand kinds from the flags.
 
-constexpr int kChunk = 256;   // instructions per staged chunk (2 KiB)
+constexpr int kChunk = kBcChunk;   // instruction words per staged chunk (2 KiB); the stream is a whole number of chunks
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned int s = (unsigned int)__cvta_generic_to_shared(smem);
@@ -155,7 +156,7 @@ __device__ __forceinline__ void mr_un(const Files<P>& f, double (&acc)[P], doubl
     case BC_H_OUT + (C) * 4 + 2: { double x[P]; mr_fetch<P, 2>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break; \
     case BC_H_OUT + (C) * 4 + 3: { double x[P]; mr_fetch<P, 3>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break;
 
-template <int P>
+template <int P, bool TREE>
 __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const uint64_t* __restrict__ code, unsigned int n_instr,
                                                     const double* __restrict__ consts, unsigned int n_consts, unsigned int n_scal,
                                                     unsigned int n_wide, unsigned int all_wide) {
@@ -172,6 +173,8 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
     F.wide = reinterpret_cast<unsigned char*>(wide + (P == 1 ? tid : 2u * tid));
     F.half_stride = 16u * B;
     F.scal = scal;
+    const unsigned int wbase_s = (unsigned int)__cvta_generic_to_shared(F.wide);   // the same, as shared-window addresses
+    const unsigned int sbase_s = (unsigned int)__cvta_generic_to_shared(scal);
     const unsigned int slot16 = P * B / 2u;              // one wide slot in 16-byte units
     const unsigned int out16 = n_wide * slot16;          // the three channel slots follow the program's slots
 
@@ -196,11 +199,10 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
     for (unsigned int i = tid; i < n_consts; i += B) scal[i] = consts[i];
     if (!all_wide && tid == 0) scal[n_consts] = (double)yi;
 
-    const unsigned int n_chunks = (n_instr + kChunk - 1) / kChunk;
-    for (unsigned int i = tid; i < kChunk / 2; i += B) {   // prefetch chunk 0
-        unsigned int idx = i * 2;
-        if (idx < n_instr) cp_async16(code_s + idx, code + idx);
-    }
+    // The stream is a whole number of chunks (bytecode_for_launch): all but the last end with YIELD, the last
+    // is padded with END.
+    const unsigned int n_chunks = n_instr / kChunk;
+    for (unsigned int i = tid; i < kChunk / 2; i += B) cp_async16(code_s + 2 * i, code + 2 * i);   // prefetch chunk 0
     cp_async_commit();
 
     for (unsigned int c = 0; c < n_chunks; c++) {
@@ -209,25 +211,27 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
         if (c + 1 < n_chunks) {
             uint64_t* dst = code_s + ((c + 1) & 1) * kChunk;
             const uint64_t* src = code + (size_t)(c + 1) * kChunk;
-            unsigned int left = n_instr - (c + 1) * kChunk;
-            for (unsigned int i = tid; i < kChunk / 2; i += B) {
-                unsigned int idx = i * 2;
-                if (idx < left) cp_async16(dst + idx, src + idx);
-            }
+            for (unsigned int i = tid; i < kChunk / 2; i += B) cp_async16(dst + 2 * i, src + 2 * i);
             cp_async_commit();
         }
         const uint64_t* cs = code_s + (c & 1) * kChunk;
-        const unsigned int cnt = (n_instr - c * kChunk < (unsigned)kChunk) ? (n_instr - c * kChunk) : (unsigned)kChunk;
-        // (Reading one word past the chunk's last instruction is harmless: the word after buffer 0 is buffer
-        // 1's first, the word after buffer 1 is the staging tile -- both inside this block's shared memory.)
-        const uint64_t* pc = cs;
-        uint64_t wn = *pc;
-        for (unsigned int i = 0; i < cnt; i++) {
-            const uint64_t w = wn;
-            wn = *++pc;                                    // next word: its latency hides behind this instruction
+        const unsigned int cs_s = (unsigned int)__cvta_generic_to_shared(cs);
+        unsigned int pc = cs_s;                            // shared-window address of the current instruction word
+        for (;;) {
+            // Inner loop (inline PTX, interp_dispatch.inc): fetch, indexed branch into a body specialised on
+            // operation and operand kinds, store, next -- until an instruction it has no body for.
+            if constexpr (!TREE) {
+                if constexpr (P == 1) MR_INTERP_LOOP_P1(acc[0], sacc, pc, wbase_s, sbase_s, F.half_stride);
+                else if constexpr (P == 2) MR_INTERP_LOOP_P2(acc[0], acc[1], sacc, pc, wbase_s, sbase_s, F.half_stride);
+                else MR_INTERP_LOOP_P4(acc[0], acc[1], acc[2], acc[3], sacc, pc, wbase_s, sbase_s, F.half_stride);
+            }
+            // One instruction through the C++ switch, which implements EVERY handler (with TREE: all of them).
+            const uint64_t w = cs[(pc - cs_s) >> 3];
+            pc += 8u;
             const unsigned int lo = (unsigned int)w, hi = (unsigned int)(w >> 32);
             const unsigned int h = lo & 0xffu;
-            const unsigned int a = hi & 0xffffu, b = hi >> 16;   // pre-scaled by the host: see Files
+            const unsigned int a = hi & 0xffffu, b = hi >> 16;   // wide indices pre-scaled by the host: see Files
+            if (h <= BC_H_YIELD) break;                          // YIELD: next chunk; END: the last chunk is done
             if (h < BC_H_SCALAR) {
                 switch (h) {
                     MR_BIN_CASES(0, OpAdd)
@@ -255,14 +259,17 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
 #pragma unroll
                     for (int k = 0; k < P; k++) acc[k] = mr_tex(t.data, t.w, t.h, imm & 3u, x[k], y[k]);
                 } break;
-                default: break;   // BC_H_END
+                default: break;
                 }
-                if (lo & (BC_F_STORE << 8)) F.store(lo >> 16, acc);
+                if ((lo & (BC_F_STORE << 8)) && h != BC_H_TEX) F.store(lo >> 16, acc);
             } else {
                 // scalar shape: one value per block, operands from the scalar file or the scalar accumulator
                 const double x = ((lo >> (8 + BC_F_KA_SHIFT)) & 3u) == BC_K_T ? sacc : scal[a];
                 const double y = ((lo >> (8 + BC_F_KB_SHIFT)) & 3u) == BC_K_T ? sacc : scal[b];
-                switch (h - BC_H_SCALAR) {
+                const unsigned int op = h < BC_H_SUN ? BC_ADD + ((h - BC_H_SBIN) >> 2)
+                                      : h < BC_H_STEX ? (((h - BC_H_SUN) >> 1) == 8u ? (unsigned)BC_MOV : BC_NEG + ((h - BC_H_SUN) >> 1))
+                                                      : (unsigned)BC_TEX;
+                switch (op) {
                 case BC_MOV: sacc = x; break;
                 case BC_ADD: sacc = x + y; break;
                 case BC_MUL: sacc = x * y; break;
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
                 } break;
                 default: break;
                 }
-                if ((lo & (BC_F_STORE << 8)) && (h - BC_H_SCALAR) != BC_TEX) scal[lo >> 16] = sacc;   // same bits from every lane
+                if ((lo & (BC_F_STORE << 8)) && op != BC_TEX) scal[lo >> 16] = sacc;   // same bits from every lane
             }
         }
     }
@@ -327,19 +334,19 @@ size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, uns
            (size_t)(n_wide + 3u) * pixels_per_thread * block * sizeof(double);   // + 3 channel-output slots
 }
 
-template <int P>
+template <int P, bool TREE>
 static cudaError_t launch_interp_as(const MrTileParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
                                     unsigned int n_consts, unsigned int n_scal, unsigned int n_wide, bool all_wide,
                                     unsigned int block, unsigned int grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(maray_interp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(maray_interp<P, TREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    maray_interp<P><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide ? 1u : 0u);
+    maray_interp<P, TREE><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide ? 1u : 0u);
     return cudaGetLastError();
 }
 
 cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
                           unsigned int n_consts, unsigned int n_uniform, unsigned int n_wide, bool all_wide, unsigned int block,
-                          unsigned int pixels_per_thread, cudaStream_t stream) {
+                          unsigned int pixels_per_thread, cudaStream_t stream, bool tree_dispatch) {
     if (p.rows == 0 || p.x1 <= p.x0) return cudaSuccess;
     const unsigned int n_scal = n_consts + n_uniform;
     const size_t smem = interp_smem_bytes(block, pixels_per_thread, n_wide, n_scal);
@@ -347,12 +354,16 @@ cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n
     p.nxb = (p.x1 - p.x0 + span - 1) / span;
     if ((uint64_t)p.nxb * p.rows > 0x7fffffffull) return cudaErrorInvalidValue;
     const unsigned int grid = p.nxb * p.rows;
+#define MR_LAUNCH(PP)                                                                                                         \
+    (tree_dispatch ? launch_interp_as<PP, true>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream) \
+                   : launch_interp_as<PP, false>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream))
     switch (pixels_per_thread) {
-    case 1: return launch_interp_as<1>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream);
-    case 2: return launch_interp_as<2>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream);
-    case 4: return launch_interp_as<4>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream);
+    case 1: return MR_LAUNCH(1);
+    case 2: return MR_LAUNCH(2);
+    case 4: return MR_LAUNCH(4);
     default: return cudaErrorInvalidValue;
     }
+#undef MR_LAUNCH
 }
 
 // ------------------------------------------------------------------------------------------------

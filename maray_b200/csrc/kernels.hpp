@@ -26,10 +26,12 @@ namespace maray {
 // Dynamic shared memory the interpreter needs for a launch configuration (n_scal = constants + row-uniform slots).
 size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, unsigned int n_wide, unsigned int n_scal);
 
-// d_code must be padded to an even number of instructions (16-byte cp.async granules).
+// d_code / n_instr: the stream made by bytecode_for_launch (a whole number of kBcChunk-word chunks).
 cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
                           unsigned int n_consts, unsigned int n_uniform, unsigned int n_wide, bool all_wide, unsigned int block,
-                          unsigned int pixels_per_thread, cudaStream_t stream);
+                          unsigned int pixels_per_thread, cudaStream_t stream, bool tree_dispatch = false);
+// tree_dispatch: run every handler through the C++ switch (nvcc lowers it to a compare-and-branch tree) instead of
+// the inline-PTX jump table -- an A/B and debugging aid (MARAY_INTERP_DISPATCH=tree).
 
 cudaError_t launch_fp64_issue_rate(bool fma, double* d_sink, int iters, int blocks, cudaStream_t stream);
 

@@ -179,11 +179,24 @@ def textured(w: int = 3840, h: int = 2160, n_tex: int = 4) -> bytes:
 def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, window: int = 192) -> bytes:
     """Seeded random DAG of about `n_values` non-constant values, >= 30 % of them sin/exp/ln.
 
-    Leaves u = x/w, v = y/h.  Every new value combines one or two earlier values taken from a sliding
-    window (so the DAG is deep, and the number of simultaneously live values stays near `window`):
-        sin(k*p + c)   sin(k1*p + k2*q + c)   exp(-(p*p))   ln(1 + p*p)   p*q   (p+q)/2
-    all of which map [-1,1] into [-1,1], so nothing overflows.  Values nobody consumed by the time they
-    leave the window are added to one of three running channel sums; channel = 127.5 + 127.5 * clamp(sum/len, -1, 1) via min/max.
+    Leaves u = x/w, v = y/h and 64 "phase fields" L_i = a_i*u + b_i*v + c_j (8 directions x 8 offsets, shared by
+    the whole program).  Every new value combines one or two
+    earlier values p, q taken from a sliding window (so the DAG is deep, and the number of simultaneously
+    live values stays near `window`):
+        sin(k*p + L_i)              k  in {1/8 .. 8/8}
+        sin(k1*p + k2*q + L_i)      k1, k2 in {1/16 .. 8/16}
+        exp(-(p*p))    ln(1 + p*p)    p*q    (p+q)/2
+    All of them map [-1,1] into [-1,1], and -- the point of this generator -- none of them EXPANDS: the
+    derivative with respect to an earlier value is at most 1 in magnitude (|k| <= 1, k1 + k2 <= 1,
+    |2p exp(-p^2)| <= 0.86, |2p/(1+p^2)| <= 1), so a last-bit difference in one sin/exp/ln result stays a
+    last-bit difference thousands of levels later.  (Round 1's generator used sin(k*p + c) with k up to 4.5: its
+    values double their sensitivity every few levels, at 1e5 values a 1-ULP nudge of the libm results moves the
+    channels by whole grey levels, and no two libms -- glibc versions included -- agree on such an image; see
+    tests/test_host_lowering.py::test_deep_scene_is_well_conditioned.)  Position enters every sine through L_i,
+    so deep values still vary over the image.
+    Values nobody consumed by the time they leave the window are added to one of three running channel sums;
+    channel = 127.5 + 127.5 * clamp(sin(40 * mean), -1, 1) via min/max (the mean of thousands of values varies
+    little; the sine spreads it over the grey range without saturating).
     """
     rng = Lcg(seed)
     u, v = E.div(E.x(), E.nat(w)), E.div(E.y(), E.nat(h))
@@ -192,9 +205,12 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
         n = rng.between(lo, hi)
         return E.div(E.nat(n), E.nat(den)) if n >= 0 else E.neg(E.div(E.nat(-n), E.nat(den)))
 
+    dirs = [E.add(E.mul(rat(1, 40, 1), u), E.mul(rat(1, 40, 1), v)) for _ in range(8)]
+    offs = [rat(0, 628, 100) for _ in range(8)]
+    phases = [E.add(d, c) for d in dirs for c in offs]
     pool: List[E.Expr] = []
     uses: List[int] = []
-    count = 0
+    count = 8 * 3 + 64
     for _ in range(16):
         f = E.sin(E.add(E.add(E.mul(rat(1, 40, 1), u), E.mul(rat(1, 40, 1), v)), rat(0, 628, 100)))
         pool.append(f); uses.append(0); count += 6
@@ -224,14 +240,16 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
         kind = rng.below(100)
         i = pick(); p = pool[i]; uses[i] += 1
         if kind < 32:
-            nv = E.sin(E.add(E.mul(rat(1, 9, 2), p), rat(0, 628, 100))); count += 3
+            ph = phases[rng.below(len(phases))]
+            nv = E.sin(E.add(E.mul(rat(1, 8, 8), p), ph)); count += 3
         elif kind < 58:
             nv = E.exp(E.neg(E.mul(p, p))); count += 3
         elif kind < 84:
             nv = E.ln(E.add(E.nat(1), E.mul(p, p))); count += 3
         elif kind < 92:
             j = pick(); q = pool[j]; uses[j] += 1
-            nv = E.sin(E.add(E.add(E.mul(rat(1, 9, 2), p), E.mul(rat(1, 9, 2), q)), rat(0, 628, 100))); count += 5
+            ph = phases[rng.below(len(phases))]
+            nv = E.sin(E.add(E.add(E.mul(rat(1, 8, 16), p), E.mul(rat(1, 8, 16), q)), ph)); count += 5
         elif kind < 96:
             j = pick(); q = pool[j]; uses[j] += 1
             nv = E.mul(p, q); count += 1
@@ -251,7 +269,7 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
     for c in range(3):
         acc = sums[c] if sums[c] is not None else pool[-1 - c]
         mean = E.div(acc, E.nat(max(1, n_summed[c])))
-        cl = E.max(E.neg(E.nat(1)), E.min(E.nat(1), mean))
+        cl = E.max(E.neg(E.nat(1)), E.min(E.nat(1), E.sin(E.mul(E.nat(40), mean))))
         half255 = E.div(E.nat(255), E.nat(2))
         chans.append(E.add(half255, E.mul(half255, cl)))
     return E.to_bytes([w, h], E.share_let(chans, bind=named))

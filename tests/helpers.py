@@ -50,7 +50,26 @@ static inline unsigned char __ldg(const unsigned char* p) { return *p; }
 static inline double __ldg(const double* p) { return *p; }
 static inline double __longlong_as_double(long long b) { double d; std::memcpy(&d, &b, 8); return d; }
 static inline void __syncthreads() {}
-using std::fabs; using std::sin; using std::exp; using std::log; using std::fmax; using std::fmin;
+using std::fabs; using std::fmax; using std::fmin;
+#ifdef MR_HOST_PERTURB_LIBM
+// Conditioning probe: every sin/exp/log result is moved by -1, 0 or +1 unit in the last place (chosen by a
+// hash of the argument).  A scene whose bytes survive this is insensitive to which libm evaluates it.
+static inline double mr_nudge(double v, double x) {
+    if (!(v - v == 0.0) || v == 0.0) return v;
+    unsigned long long b, hsh; std::memcpy(&b, &v, 8); std::memcpy(&hsh, &x, 8);
+    hsh *= 0x9E3779B97F4A7C15ull; hsh ^= hsh >> 29;
+    b += (unsigned long long)((long long)(hsh % 3) - 1);
+    std::memcpy(&v, &b, 8); return v;
+}
+static inline double mr_host_sin(double x) { return mr_nudge(std::sin(x), x); }
+static inline double mr_host_exp(double x) { return mr_nudge(std::exp(x), x); }
+static inline double mr_host_log(double x) { return mr_nudge(std::log(x), x); }
+#define sin mr_host_sin
+#define exp mr_host_exp
+#define log mr_host_log
+#else
+using std::sin; using std::exp; using std::log;
+#endif
 """
 
 HOST_DRIVER = r"""
@@ -88,14 +107,17 @@ class _Tex(ctypes.Structure):
 _CACHE = {}
 
 
-def host_jit_run(source: str, w: int, p0: int, n: int, textures=()):
-    """Runs the generated kernel text on the CPU.  Returns (rgb uint8 (n,3), planes float64 (3,n))."""
-    key = hashlib.sha256(source.encode()).hexdigest()
+def host_jit_run(source: str, w: int, p0: int, n: int, textures=(), perturb_libm: bool = False):
+    """Runs the generated kernel text on the CPU.  Returns (rgb uint8 (n,3), planes float64 (3,n)).
+    perturb_libm: every sin/exp/log result is moved by up to one unit in the last place (conditioning probe)."""
+    key = hashlib.sha256(source.encode()).hexdigest() + ("p" if perturb_libm else "")
     lib = _CACHE.get(key)
     if lib is None:
         d = tempfile.mkdtemp(prefix="maray_hostjit_")
         src = os.path.join(d, "k.cpp")
         with open(src, "w") as f:
+            if perturb_libm:
+                f.write("#define MR_HOST_PERTURB_LIBM 1\n")
             f.write(HOST_SHIM)
             if "maray_pre_x" in source:
                 f.write("#define MR_HOST_HAS_PROLOGUE 1\n")
@@ -127,7 +149,7 @@ def host_jit_run(source: str, w: int, p0: int, n: int, textures=()):
 (BC_END, BC_MOV, BC_ADD, BC_MUL, BC_MAX, BC_MIN, BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,
  BC_TEX, BC_OUT_R, BC_OUT_G, BC_OUT_B) = range(18)
 K_A, K_W, K_S, K_T = 0, 1, 2, 3
-H_END, H_BIN, H_UN, H_OUT, H_TEX, H_SCALAR = 0, 16, 80, 116, 128, 144
+H_END, H_BIN, H_UN, H_OUT, H_TEX, H_SCALAR, H_SBIN, H_SUN, H_STEX, H_COUNT = 0, 16, 80, 116, 128, 144, 144, 160, 178, 179
 F_STORE, F_KA_SHIFT, F_KB_SHIFT = 1, 2, 4
 
 
@@ -142,9 +164,17 @@ def bc_decode(w):
     if h == H_END:
         return False, BC_END, 0, 0, False, 0, 0, 0
     if h >= H_SCALAR:
-        op = h - H_SCALAR
-        assert BC_MOV <= op <= BC_TEX and ka in (K_S, K_T), "scalar instruction with a wide operand"
-        assert kb in (K_S, K_T) or not (BC_ADD <= op <= BC_MIN or op == BC_TEX)
+        assert h < H_COUNT and ka in (K_S, K_T), "scalar instruction with a wide operand"
+        if h < H_SUN:
+            op = BC_ADD + (h - H_SBIN) // 4
+            assert kb in (K_S, K_T) and (h - H_SBIN) % 4 == (ka == K_T) * 2 + (kb == K_T), "handler id and flags disagree"
+        elif h < H_STEX:
+            u = (h - H_SUN) // 2
+            op = BC_MOV if u == 8 else BC_NEG + u
+            assert (h - H_SUN) % 2 == (ka == K_T), "handler id and flags disagree"
+        else:
+            op = BC_TEX
+            assert kb in (K_S, K_T)
         return True, op, ka, kb, store, dst, a, b
     if H_BIN <= h < H_UN:
         op = BC_ADD + (h - H_BIN) // 16

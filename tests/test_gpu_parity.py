@@ -177,7 +177,8 @@ def test_texture_edges_and_out_of_range(backend):
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_deep_transcendental_scene_within_tolerance(backend):
     """Config 5 shape at a size the oracle finishes: >= 99.99 % identical bytes, rest within 1 LSB;
-    f64 values within 1e-12 relative (CUDA sin/exp/log are <= 2/1/1 ULP; errors compound over depth)."""
+    f64 channel values within 1e-10 of the oracle's on the 0..255 scale (the device sin/exp/log are <= 1.5/0.9/0.6
+    ULP; the generator's maps never expand a difference, the final 127.5*sin(40*mean) scales it by ~5000)."""
     scene = scenes.deep(192, 128, n_values=500, seed=7)
     w, h = 192, 128
     want_rgb, want = OracleScene(scene).render_window(0, w, 0, h, want_f64=True)
@@ -188,8 +189,7 @@ def test_deep_transcendental_scene_within_tolerance(backend):
     n_diff, n_bad = _attribute_mismatches(scene, rgb, want_rgb)
     assert n_bad == 0, "a channel differs from the oracle by more than 1 LSB"
     assert n_diff <= max(1, w * h // 10000)
-    rel = np.abs(planes - want) / np.maximum(np.abs(want), 1e-300)
-    assert np.nanmax(rel) < 1e-12
+    assert np.nanmax(np.abs(planes - want)) < 1e-10
 
 
 def _heavy_scene_with_out_of_range_arguments(w, h):
@@ -342,8 +342,8 @@ def _windows_and_rows_vs_oracle(r, oracle, w, h, windows, rows, exact, frame=Non
             _assert_flips_are_step_boundaries(oracle, rgb, want_rgb, x0, y0)
             n_diff += int((rgb != want_rgb).any(axis=2).sum())
             close = (np.abs(rgb.astype(np.int16) - want_rgb.astype(np.int16)) <= 1).transpose(2, 0, 1)   # not a step flip
-            ok = np.isfinite(want) & (np.abs(want) > 1e-9) & close
-            assert np.nanmax(np.abs(planes[ok] - want[ok]) / np.abs(want[ok]), initial=0.0) < 1e-9
+            ok = np.isfinite(want) & close
+            assert np.nanmax(np.abs(planes[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1.0), initial=0.0) < 1e-9
         n_px += ww * hh
     if rows:
         want_rows = oracle.render_rows(rows, w)
@@ -453,15 +453,16 @@ def test_interpreter_row_uniform_form(monkeypatch):
 
 
 def test_pipelined_host_render(monkeypatch):
-    """MARAY_PIPELINE=1: the frame is rendered in row chunks whose device->host copies overlap the next
-    chunks; same bytes as the plain render, on a frame above the 4 MiB threshold and an odd-sized one."""
+    """Host-bound frames of 4 MiB and more are rendered in row chunks whose device->host copies overlap the
+    next chunks (the default; MARAY_PIPELINE=0 is the plain render): same bytes either way, on a frame above
+    the threshold and an odd-sized one."""
     for scene, w, h in [(scenes.sdf(), 1920, 1080), (scenes.sdf(1501, 1203, 9, seed=2), 1501, 1203)]:
         with _renderer(scene, "nvrtc") as r:
+            monkeypatch.setenv("MARAY_PIPELINE", "0")
             base = r.render(w, h)
-            monkeypatch.setenv("MARAY_PIPELINE", "1")
+            monkeypatch.delenv("MARAY_PIPELINE")
             got = r.render(w, h)
             got2 = r.render(w, h)
-            monkeypatch.delenv("MARAY_PIPELINE")
         assert np.array_equal(got, base) and np.array_equal(got2, base)
         want_rows = OracleScene(scene).render_rows([0, h // 2, h - 1], w)
         for i, y in enumerate([0, h // 2, h - 1]):

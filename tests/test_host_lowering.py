@@ -71,6 +71,27 @@ def test_deep_scene_bit_exact():
     _check_scene(scenes.deep(96, 64, n_values=600, seed=4), 96, [0, 33])
 
 
+def test_deep_scene_is_well_conditioned(monkeypatch):
+    """The deep benchmark scene must not amplify last-bit differences between libms: with every sin/exp/log
+    result nudged by up to one unit in the last place (tests/helpers.py, perturb_libm) the bytes stay the same
+    and the channel values move by less than 1e-9 of a grey level.  (Round 1's generator failed this badly: its
+    sin(k*p + c) with k up to 4.5 doubled the sensitivity every few levels -- 8e-11 relative at 12 000 values,
+    1e-5 at 40 000, whole grey levels at 100 000 -- so no two libms could agree on its image.)"""
+    monkeypatch.setenv("MARAY_JIT_SOURCE_ONLY", "1")
+    scene = scenes.deep(64, 64, n_values=12000, seed=5)
+    with CudaRenderer(gpus=0) as r:
+        r.load(scene)
+        with pytest.raises(Exception):
+            r.compile("nvrtc")              # MARAY_JIT_SOURCE_ONLY: the text is generated, NVRTC is not run
+        src, st = r.source(), r.stats()
+    assert st["dag_depth"] > 250 and (st["n_sin"] + st["n_exp"] + st["n_ln"]) / (st["dag_nodes"] - st["n_const"]) >= 0.28
+    rgb, planes = host_jit_run(src, 64, 64 * 10, 64)
+    rgb_n, planes_n = host_jit_run(src, 64, 64 * 10, 64, perturb_libm=True)
+    assert np.array_equal(rgb, rgb_n)
+    assert np.abs(planes - planes_n).max() < 1e-9
+    assert rgb.std() > 20                                   # and it is an image, not a grey card
+
+
 def test_segmented_source_matches_unsegmented(monkeypatch):
     scene = scenes.deep(64, 64, n_values=900, seed=11)
     srcs = []
@@ -246,6 +267,7 @@ def test_transcendental_batching_keeps_values(monkeypatch, form):
     if form == "separate_units":
         monkeypatch.setenv("MARAY_JIT_PARALLEL", "1")
         monkeypatch.setenv("MARAY_JIT_SEGMENT_VALUES", "4096")
+        monkeypatch.setenv("MARAY_JIT_CACHE", "off")          # the compile and link statistics below are those of a real compile
     scene = scenes.deep(48, 32, n_values=9000, seed=3)
     with CudaRenderer(gpus=0) as r:
         r.load(scene)
