@@ -441,7 +441,7 @@ def run_ours(args):
                         "nvrtc_ms": stats["nvrtc_ms"], "load_ms": stats["load_ms"], "wall_s": compile_s,
                         "registers": stats["jit_registers"], "segments": stats["jit_segments"],
                         "units": stats["jit_units"], "compile_threads": stats["jit_compile_threads"],
-                        "link_ms": stats["link_ms"], "cache_hit": bool(stats["jit_cache_hit"]),
+                        "cache_hit": bool(stats["jit_cache_hit"]),
                         "interp_instructions": stats["interp_instructions"], "interp_slots": stats["interp_slots"]},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -65,22 +65,21 @@ typedef struct maray_cuda_stats {
     uint32_t backend;
     uint32_t interp_instructions; /* bytecode length (interpreter back end)                          */
     uint32_t interp_slots;        /* per-pixel (wide) value slots the bytecode needs                 */
-    uint32_t jit_segments;        /* device functions the generated source was cut into              */
-    uint32_t jit_frame_slots;     /* per-thread frame doubles (0 when not segmented)                 */
+    uint32_t jit_segments;        /* parts the generated program was cut into (chain form: kernels)  */
+    uint32_t jit_frame_slots;     /* doubles per pixel that cross a cut (0 when not segmented)       */
     uint32_t jit_registers;       /* registers per thread of the generated kernel (0 = unknown)      */
     uint32_t jit_source_bytes;
     uint32_t jit_cubin_bytes;
-    uint32_t jit_units;           /* translation units compiled (1, or 1 + segments when linked)     */
+    uint32_t jit_units;           /* translation units compiled (1, or one per segment kernel)       */
     uint32_t jit_compile_threads; /* host threads that ran NVRTC concurrently (0 on a cache hit)     */
-    uint32_t jit_cache_hit;       /* 1 when the cubin came from the MARAY_JIT_CACHE directory        */
+    uint32_t jit_cache_hit;       /* 1 when every cubin came from the cache directory                */
     uint32_t interp_uniform_slots;/* per-block row-uniform scalar slots (interpreter; 0 in the all-wide form) */
     uint32_t interp_block;        /* interpreter launch shape: threads per block ...                 */
     uint32_t interp_pixels_per_thread; /* ... and pixels per thread (a block spans block*ppt pixels of one row) */
     /* timings, milliseconds */
     double lower_ms;              /* Expr -> SSA                                                     */
     double codegen_ms;            /* SSA -> source / bytecode                                        */
-    double nvrtc_ms;              /* NVRTC compile incl. link (reported separately from render time) */
-    double link_ms;               /* nvJitLink share of nvrtc_ms (0 for a single translation unit)   */
+    double nvrtc_ms;              /* NVRTC compile, all units (reported separately from render time) */
     double load_ms;               /* cubin load + uploads                                            */
     double kernel_ms[8];          /* last render: device time of the band kernel, per GPU            */
     double gather_ms;             /* last render: band gather to GPU 0 (peer copies)                 */
@@ -149,6 +148,10 @@ int maray_cuda_get_stats(const maray_cuda_t* h, maray_cuda_stats* stats);
 /* Generated CUDA source of the NVRTC back end (after compile).  Returns its length in *len; copies
  * at most cap bytes (NUL-terminated when cap > 0). */
 int maray_cuda_get_source(const maray_cuda_t* h, char* buf, size_t cap, size_t* len);
+/* The translation units NVRTC actually compiled for the last scene (stats.jit_units of them; for a program
+ * above the segment size one kernel per segment, launched in order -- see stats.jit_segments).  Same calling
+ * convention as maray_cuda_get_source; MARAY_E_INVALID when `index` is out of range. */
+int maray_cuda_get_module(const maray_cuda_t* h, uint32_t index, char* buf, size_t cap, size_t* len);
 /* Bytecode of the interpreter back end: 8-byte instructions, then the constant pool. */
 int maray_cuda_get_bytecode(const maray_cuda_t* h, uint64_t* code, size_t cap_instr, size_t* n_instr,
                             double* consts, size_t cap_consts, size_t* n_consts);

@@ -28,7 +28,7 @@ class Stats(ctypes.Structure):
             "jit_units", "jit_compile_threads", "jit_cache_hit", "interp_uniform_slots", "interp_block",
             "interp_pixels_per_thread")]
         + [("lower_ms", ctypes.c_double), ("codegen_ms", ctypes.c_double), ("nvrtc_ms", ctypes.c_double),
-           ("link_ms", ctypes.c_double), ("load_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double * 8), ("gather_ms", ctypes.c_double),
+           ("load_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double * 8), ("gather_ms", ctypes.c_double),
            ("d2h_ms", ctypes.c_double), ("render_ms", ctypes.c_double)]
     )
 
@@ -59,6 +59,7 @@ SYMBOLS = [
     ("maray_cuda_render_window_f64", ctypes.c_int, [_P] + [ctypes.c_uint32] * 6 + [_P, _P]),
     ("maray_cuda_get_stats", ctypes.c_int, [_P, ctypes.POINTER(Stats)]),
     ("maray_cuda_get_source", ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    ("maray_cuda_get_module", ctypes.c_int, [_P, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     ("maray_cuda_get_bytecode", ctypes.c_int, [_P, _P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), _P,
                                                ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     ("maray_cuda_fp64_peak", ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),

@@ -59,9 +59,10 @@ struct Gpu {
     std::vector<uint8_t*> d_tex;
     MrTexture* d_textab = nullptr;
     // back ends
-    cudaLibrary_t lib = nullptr;
-    cudaKernel_t jit_kernel = nullptr;
+    std::vector<cudaLibrary_t> libs;                   // one per translation unit (chain form: one per segment)
+    std::vector<cudaKernel_t> jit_kernels;             // the kernel of each unit, in launch order
     cudaKernel_t jit_pre_x = nullptr, jit_pre_y = nullptr;
+    double* d_frame = nullptr; size_t frame_cap = 0;   // chain form: values crossing segment cuts, F[slot * FS + pixel]
     double* d_colv = nullptr; size_t colv_cap = 0;     // hoisting tables (doubles)
     double* d_rowv = nullptr; size_t rowv_cap = 0;
     cudaEvent_t hoist_done = nullptr;                  // last launch that read the tables (they are per GPU, not per stream)
@@ -85,15 +86,16 @@ struct maray_cuda {
     int backend = -1;
     std::string source;                 // the kernel's translation unit (== modules[0])
     std::vector<std::string> modules;   // every translation unit of the last NVRTC compile
-    std::vector<char> cubin;
+    std::vector<std::vector<char>> cubins;   // one per translation unit
     Bytecode bc;
     std::vector<uint64_t> bc_device;                   // bc.code with operand fields scaled for the launch shape
     unsigned interp_block = 128, interp_ppt = 2;       // launch shape: threads per block, pixels per thread
-    bool interp_tree = false;                          // MARAY_INTERP_DISPATCH=tree: C++ switch instead of the jump table (A/B)
+    int interp_dispatch = 0;                           // MARAY_INTERP_DISPATCH=tree|private (kernels.hpp launch_interp), A/B
     unsigned jit_block = 256;
     unsigned jit_dyn_smem = 0;                         // dynamic shared memory of the generated kernel
     unsigned jit_maxreg = 0;
-    unsigned jit_link_maxreg = 0;                      // register cap of separately compiled segment functions
+    bool jit_chain = false;                            // one kernel per segment, launched in order over a global frame
+    unsigned jit_frame_slots = 0;
     unsigned jit_ncol = 0, jit_nrow = 0;               // hoisted values per column / per row
     maray_cuda_stats stats{};
     int report_kind = MARAY_REPORT_NONE;
@@ -120,7 +122,9 @@ int fail(maray_cuda* h, int code, const std::string& msg) {
 void release_backend(maray_cuda* h) {
     for (Gpu& g : h->gpus) {
         cudaSetDevice(g.device);
-        if (g.lib) { cudaLibraryUnload(g.lib); g.lib = nullptr; g.jit_kernel = nullptr; g.jit_pre_x = g.jit_pre_y = nullptr; }
+        for (cudaLibrary_t l : g.libs) cudaLibraryUnload(l);
+        g.libs.clear(); g.jit_kernels.clear(); g.jit_pre_x = g.jit_pre_y = nullptr;
+        if (g.d_frame) { cudaFree(g.d_frame); g.d_frame = nullptr; g.frame_cap = 0; }
         if (g.d_colv) { cudaFree(g.d_colv); g.d_colv = nullptr; g.colv_cap = 0; }
         if (g.d_rowv) { cudaFree(g.d_rowv); g.d_rowv = nullptr; g.rowv_cap = 0; }
         if (g.d_code) { cudaFree(g.d_code); g.d_code = nullptr; }
@@ -187,59 +191,9 @@ void fill_program_stats(maray_cuda* h) {
 
 // ---- NVRTC: source -> sm_100a cubin.  Works without a GPU. ----------------------------------------
 //
-// One translation unit is compiled straight to a cubin.  Several (generate_cuda_modules: the kernel's
-// unit plus one unit per segment function) are compiled concurrently, one NVRTC program per host
-// thread, with --relocatable-device-code, and linked into one cubin by nvJitLink.  The finished
-// cubin can be kept in a directory (MARAY_JIT_CACHE) keyed by the generated text and the options.
-
-// nvJitLink is bound at run time, by path: a process that already holds another libnvJitLink.so.12
-// (PyTorch bundles its own, one minor version older than this toolkit's) would otherwise hand that
-// one to us, and a linker older than the compiler that produced the objects is not supported.  The
-// `_12_0` entry points exist in every 12.x release.
-struct JitLink {
-    typedef int (*create_fn)(void**, uint32_t, const char**);
-    typedef int (*destroy_fn)(void**);
-    typedef int (*add_fn)(void*, int, const void*, size_t, const char*);
-    typedef int (*complete_fn)(void*);
-    typedef int (*size_fn)(void*, size_t*);
-    typedef int (*get_fn)(void*, void*);
-    typedef int (*getlog_fn)(void*, char*);
-    create_fn create = nullptr; destroy_fn destroy = nullptr; add_fn add = nullptr; complete_fn complete = nullptr;
-    size_fn cubin_size = nullptr; get_fn cubin = nullptr; size_fn log_size = nullptr; getlog_fn log = nullptr;
-    std::string where;
-    static constexpr int kInputCubin = 1;   // NVJITLINK_INPUT_CUBIN
-
-    static const JitLink* get() {
-        static const JitLink* inst = [] () -> const JitLink* {
-            std::vector<std::string> paths;
-            if (const char* e = std::getenv("MARAY_NVJITLINK")) paths.push_back(e);
-            if (const char* e = std::getenv("CUDA_HOME")) paths.push_back(std::string(e) + "/lib64/libnvJitLink.so.12");
-            paths.push_back("/usr/local/cuda/lib64/libnvJitLink.so.12");
-            paths.push_back("libnvJitLink.so.12");
-            for (const std::string& p : paths) {
-                void* so = dlopen(p.c_str(), RTLD_NOW | RTLD_LOCAL);
-                if (!so) continue;
-                JitLink* j = new JitLink;
-                j->create = reinterpret_cast<create_fn>(dlsym(so, "__nvJitLinkCreate_12_0"));
-                j->destroy = reinterpret_cast<destroy_fn>(dlsym(so, "__nvJitLinkDestroy_12_0"));
-                j->add = reinterpret_cast<add_fn>(dlsym(so, "__nvJitLinkAddData_12_0"));
-                j->complete = reinterpret_cast<complete_fn>(dlsym(so, "__nvJitLinkComplete_12_0"));
-                j->cubin_size = reinterpret_cast<size_fn>(dlsym(so, "__nvJitLinkGetLinkedCubinSize_12_0"));
-                j->cubin = reinterpret_cast<get_fn>(dlsym(so, "__nvJitLinkGetLinkedCubin_12_0"));
-                j->log_size = reinterpret_cast<size_fn>(dlsym(so, "__nvJitLinkGetErrorLogSize_12_0"));
-                j->log = reinterpret_cast<getlog_fn>(dlsym(so, "__nvJitLinkGetErrorLog_12_0"));
-                if (j->create && j->destroy && j->add && j->complete && j->cubin_size && j->cubin && j->log_size && j->log) {
-                    j->where = p;
-                    return j;
-                }
-                delete j;
-                dlclose(so);
-            }
-            return nullptr;
-        }();
-        return inst;
-    }
-};
+// Every translation unit is compiled straight to its own cubin; several (the chain form of a large program:
+// one kernel per segment) are compiled concurrently, one NVRTC program per host thread, and nothing is
+// linked.  Finished cubins are kept in a directory (jit_cache_dir) keyed by the unit's text and the options.
 
 struct UnitResult {
     nvrtcResult rc = NVRTC_SUCCESS;
@@ -277,7 +231,7 @@ void compile_unit(const std::string& source, const std::vector<std::string>& opt
 }
 
 // 128-bit FNV-1a style key over the generated text and the compile options.
-std::string cache_key(const std::vector<std::string>& modules, const std::vector<std::string>& options) {
+std::string cache_key(const std::string& module, const std::vector<std::string>& options) {
     uint64_t a = 0xcbf29ce484222325ull, b = 0x84222325cbf29ce4ull;
     auto mix = [&](const std::string& t) {
         for (unsigned char c : t) {
@@ -287,7 +241,7 @@ std::string cache_key(const std::vector<std::string>& modules, const std::vector
         a = (a ^ 0xff) * 0x100000001b3ull;
         b = (b ^ 0xfe) * 0x00000100000001b5ull;
     };
-    for (const std::string& m : modules) mix(m);
+    mix(module);
     for (const std::string& o : options) mix(o);
     int major = 0, minor = 0;
     nvrtcVersion(&major, &minor);
@@ -357,7 +311,6 @@ std::string jit_cache_dir() {
 
 int nvrtc_compile(maray_cuda* h) {
     const size_t n_units = h->modules.size();
-    const bool link = n_units > 1;
     std::vector<std::string> options = {
         "--gpu-architecture=sm_100a",
         "--fmad=false",               // the reference never fuses a*b+c
@@ -365,16 +318,11 @@ int nvrtc_compile(maray_cuda* h) {
         "--ptxas-options=-v",
         "--diag-suppress=177",        // unused double shadows of boolean values: dead code by design
     };
-    // Line tables map SASS to the generated text (ncu source page).  On by default for one unit; a
-    // linked build carries one table per unit (4x the cubin, seconds of link time): MARAY_JIT_LINEINFO=1.
-    bool lineinfo = !link;
+    // Line tables map SASS to the generated text (ncu source page).
+    bool lineinfo = true;
     if (const char* e = std::getenv("MARAY_JIT_LINEINFO")) lineinfo = std::strtoul(e, nullptr, 10) != 0;
     if (lineinfo) options.push_back("-lineinfo");
-    // A separately compiled segment function does not see the kernel's __launch_bounds__: it needs the
-    // register cap spelled out, or the linked kernel inherits a larger count than the launch shape allows.
-    unsigned maxreg = h->jit_maxreg ? h->jit_maxreg : (link ? h->jit_link_maxreg : 0);
-    if (maxreg) options.push_back("--maxrregcount=" + std::to_string(maxreg));
-    if (link) options.push_back("--relocatable-device-code=true");
+    if (h->jit_maxreg) options.push_back("--maxrregcount=" + std::to_string(h->jit_maxreg));
     if (std::getenv("MARAY_JIT_NOSLOW")) options.push_back("-DMR_NO_SLOW=1");   // experiment only (wrong for huge/NaN arguments)
     if (const char* e = std::getenv("MARAY_LIBM"))      // A/B: MARAY_LIBM=cuda uses libdevice's sin/exp/log
         if (std::string(e) == "cuda") options.push_back("-DMR_LIBM_PLAIN=1");
@@ -383,38 +331,42 @@ int nvrtc_compile(maray_cuda* h) {
     h->stats.jit_units = uint32_t(n_units);
     h->stats.jit_compile_threads = 0;
     h->stats.jit_cache_hit = 0;
-    h->stats.link_ms = 0.0;
+    h->cubins.assign(n_units, {});
 
-    std::string cache_path;
+    // cache: per unit, so an edit that changes one segment recompiles one segment
     const std::string cache_dir = jit_cache_dir();
-    if (!cache_dir.empty()) {
-        cache_path = cache_dir + "/" + cache_key(h->modules, options) + ".mrcubin";
+    std::vector<std::string> cache_path(n_units);
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < n_units; i++) {
         uint32_t regs = 0;
-        if (cache_load(cache_path, &h->cubin, &regs)) {
-            h->stats.jit_registers = regs;
-            h->stats.jit_cache_hit = 1;
-            return MARAY_OK;
+        if (!cache_dir.empty()) {
+            cache_path[i] = cache_dir + "/" + cache_key(h->modules[i], options) + ".mrcubin";
+            if (cache_load(cache_path[i], &h->cubins[i], &regs)) {
+                h->stats.jit_registers = std::max(h->stats.jit_registers, regs);
+                continue;
+            }
         }
+        todo.push_back(i);
     }
+    if (todo.empty()) { h->stats.jit_cache_hit = 1; return MARAY_OK; }
 
     std::vector<UnitResult> res(n_units);
     unsigned n_threads = std::thread::hardware_concurrency();
     if (const char* e = std::getenv("MARAY_JIT_THREADS")) n_threads = unsigned(std::strtoul(e, nullptr, 10));
-    n_threads = std::max(1u, std::min<unsigned>(n_threads, unsigned(n_units)));
+    n_threads = std::max(1u, std::min<unsigned>(n_threads, unsigned(todo.size())));
     h->stats.jit_compile_threads = n_threads;
     if (n_threads == 1) {
-        for (size_t i = 0; i < n_units; i++) compile_unit(h->modules[i], options, &res[i]);
+        for (size_t i : todo) compile_unit(h->modules[i], options, &res[i]);
     } else {
-        // the kernel's unit is small; the segment units are roughly equal: a shared counter balances them
         std::atomic<size_t> next{0};
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < n_threads; t++)
             pool.emplace_back([&] {
-                for (size_t i = next.fetch_add(1); i < n_units; i = next.fetch_add(1)) compile_unit(h->modules[i], options, &res[i]);
+                for (size_t k = next.fetch_add(1); k < todo.size(); k = next.fetch_add(1)) compile_unit(h->modules[todo[k]], options, &res[todo[k]]);
             });
         for (std::thread& t : pool) t.join();
     }
-    for (size_t i = 0; i < n_units; i++) {
+    for (size_t i : todo) {
         if (res[i].rc != NVRTC_SUCCESS) {
             // the diagnostics that matter first: a long log of warnings must not push the errors out of the message
             std::string log, rest;
@@ -433,52 +385,19 @@ int nvrtc_compile(maray_cuda* h) {
             if (log.size() > 4000) log.resize(4000);
             return fail(h, MARAY_E_COMPILE, "NVRTC (unit " + std::to_string(i) + "): " + nvrtcGetErrorString(res[i].rc) + "\n" + log);
         }
-        h->stats.jit_registers = std::max(h->stats.jit_registers, res[i].max_registers);
         if (std::getenv("MARAY_JIT_VERBOSE")) std::fprintf(stderr, "%s\n", res[i].log.c_str());
-    }
-
-    if (!link) {
-        h->cubin = std::move(res[0].cubin);
-        // registers of the kernel from the ptxas -v log:
-        //   "Function properties for maray_jit" ... "Used N registers"
-        const std::string& log = res[0].log;
+        // registers of the kernel from the ptxas -v log: "Function properties for maray_jit" ... "Used N registers"
+        uint32_t regs = res[i].max_registers;
+        const std::string& log = res[i].log;
         size_t at = log.find(std::string("Function properties for ") + kJitKernelName);
         if (at != std::string::npos) {
             size_t u = log.find("Used ", at);
-            if (u != std::string::npos) h->stats.jit_registers = uint32_t(std::atoi(log.c_str() + u + 5));
+            if (u != std::string::npos) regs = uint32_t(std::atoi(log.c_str() + u + 5));
         }
-    } else {
-        double t0 = now_ms();
-        const JitLink* J = JitLink::get();
-        if (!J) return fail(h, MARAY_E_COMPILE, "libnvJitLink.so.12 not found (set MARAY_NVJITLINK, or MARAY_JIT_PARALLEL=0)");
-        void* lk = nullptr;
-        const char* lopts[] = {"-arch=sm_100a", "-lineinfo"};
-        if (J->create(&lk, lineinfo ? 2 : 1, lopts) != 0) return fail(h, MARAY_E_COMPILE, "nvJitLinkCreate failed");
-        auto link_error = [&](const char* what) {
-            size_t n = 0;
-            std::string log;
-            if (J->log_size(lk, &n) == 0 && n > 1) { log.assign(n, '\0'); J->log(lk, &log[0]); }
-            J->destroy(&lk);
-            if (log.size() > 4000) log.resize(4000);
-            return fail(h, MARAY_E_COMPILE, std::string("nvJitLink: ") + what + "\n" + log);
-        };
-        for (size_t i = 0; i < n_units; i++) {
-            std::string name = "maray_unit" + std::to_string(i);
-            if (J->add(lk, JitLink::kInputCubin, res[i].cubin.data(), res[i].cubin.size(), name.c_str()) != 0)
-                return link_error("adding a unit failed");
-        }
-        if (J->complete(lk) != 0) return link_error("link failed");
-        size_t n = 0;
-        if (J->cubin_size(lk, &n) != 0 || n == 0) return link_error("no linked cubin");
-        h->cubin.resize(n);
-        if (J->cubin(lk, h->cubin.data()) != 0) return link_error("reading the linked cubin failed");
-        J->destroy(&lk);
-        h->stats.link_ms = now_ms() - t0;
-        // The linked kernel's register count is that of its call graph; without a device to ask
-        // (maray_cuda_compile refines this after the load) the cap is what is known.
-        if (maxreg) h->stats.jit_registers = maxreg;
+        h->stats.jit_registers = std::max(h->stats.jit_registers, regs);
+        h->cubins[i] = std::move(res[i].cubin);
+        if (!cache_path[i].empty()) cache_store(cache_path[i], h->cubins[i], regs, 1);
     }
-    if (!cache_path.empty()) cache_store(cache_path, h->cubin, h->stats.jit_registers, uint32_t(n_units));
     return MARAY_OK;
 }
 
@@ -560,10 +479,43 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
             }
             p.colv = g.d_colv; p.rowv = g.d_rowv; p.row_base = y_first; p.rows = rows;
         }
-        void* args[] = {&p};
-        unsigned grid = (n + h->jit_block - 1) / h->jit_block;
-        CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernel), dim3(grid), dim3(h->jit_block), args, h->jit_dyn_smem, stream));
-        if (g.hoist_done && (h->jit_ncol || h->jit_nrow)) CU_TRY(h, cudaEventRecord(g.hoist_done, stream));
+        if (!h->jit_chain) {
+            void* args[] = {&p};
+            unsigned grid = (n + h->jit_block - 1) / h->jit_block;
+            CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernels[0]), dim3(grid), dim3(h->jit_block), args, h->jit_dyn_smem, stream));
+            if (g.hoist_done && (h->jit_ncol || h->jit_nrow)) CU_TRY(h, cudaEventRecord(g.hoist_done, stream));
+        } else {
+            // Chain form: the segment kernels run in order over a chunk of pixels whose frame (values that cross
+            // a cut, F[slot * FS + pixel]) fits the budget; chunks follow each other on the stream.
+            size_t budget = size_t(2) << 30;
+            if (const char* e = std::getenv("MARAY_JIT_FRAME_MB")) budget = std::max<size_t>(1, std::strtoull(e, nullptr, 10)) << 20;
+            const size_t per_px = std::max<size_t>(h->jit_frame_slots, 1) * sizeof(double);
+            size_t chunk = std::max<size_t>(budget / per_px, h->jit_block);
+            chunk = std::min<size_t>(chunk / h->jit_block * h->jit_block, (size_t(n) + h->jit_block - 1) / h->jit_block * h->jit_block);
+            // One frame per GPU: launches of a handle that use it are serialised across streams (like the hoisting tables).
+            if (!g.hoist_done) CU_TRY(h, cudaEventCreateWithFlags(&g.hoist_done, cudaEventDisableTiming));
+            else CU_TRY(h, cudaStreamWaitEvent(stream, g.hoist_done, 0));
+            if (g.frame_cap < chunk * per_px) {
+                if (g.d_frame) cudaFree(g.d_frame);
+                g.d_frame = nullptr; g.frame_cap = 0;
+                CU_TRY(h, cudaMalloc(&g.d_frame, chunk * per_px));
+                g.frame_cap = chunk * per_px;
+            }
+            unsigned long long fs = chunk;
+            for (size_t done = 0; done < n; done += chunk) {
+                MrParams q = p;
+                q.p0 = p0 + uint32_t(done);
+                q.n = uint32_t(std::min<size_t>(chunk, n - done));
+                q.out = d_out + 3 * done;
+                q.out_aligned = (reinterpret_cast<uintptr_t>(q.out) % 16 == 0) ? 1u : 0u;
+                if (d_f64) q.f64_out = d_f64 + done;
+                void* args[] = {&q, &g.d_frame, &fs};
+                unsigned grid = (q.n + h->jit_block - 1) / h->jit_block;
+                for (cudaKernel_t k : g.jit_kernels)
+                    CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(h->jit_block), args, h->jit_dyn_smem, stream));
+            }
+            CU_TRY(h, cudaEventRecord(g.hoist_done, stream));
+        }
     } else {
         // The interpreter renders windows [x0,x1) x rows with every block inside one row: a linear pixel range
         // is at most a partial first row, whole rows, and a partial last row.
@@ -583,7 +535,7 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
             t.out_aligned = (reinterpret_cast<uintptr_t>(t.out) % 16 == 0) ? 1u : 0u;
             CU_TRY(h, launch_interp(t, g.d_code, unsigned(h->bc_device.size()), g.d_consts, unsigned(h->bc.consts.size()),
                                     h->bc.n_uniform, h->bc.n_wide, !h->bc.row_uniform, h->interp_block, h->interp_ppt, stream,
-                                    h->interp_tree));
+                                    h->interp_dispatch));
             const uint32_t count = cols * rows;
             done += count; pix += count; left -= count;
         }
@@ -888,23 +840,17 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10));
         h->jit_maxreg = 0;
         if (const char* e = std::getenv("MARAY_JIT_MAXREG")) h->jit_maxreg = unsigned(std::strtoul(e, nullptr, 10));
-        // MARAY_JIT_PARALLEL=1: every segment function becomes its own translation unit, the units are
-        // compiled on all host cores and linked (nvrtc_compile) -- 3-5x less compile latency on large
-        // programs, but a separately compiled segment has to honour the full call ABI and the kernel
-        // runs ~20 % slower (measured on the 20 000-value deep scene: 17.6 vs 14.7 ms), so one unit is
-        // the default and MARAY_JIT_CACHE is the answer to compile latency.
-        // sin/exp/ln stay out of line above the threshold: inlined, the code
-        // of a transcendental-heavy program is several MB of instructions no warp ever re-uses, and the
-        // kernel becomes instruction-fetch bound (measured: 33.8 ms inlined vs 18.7 ms out of line on
-        // the 20 000-value deep scene, no_instruction stalls 9.1 per issued instruction; profiles/).
-        bool parallel = false;
-        if (const char* e = std::getenv("MARAY_JIT_PARALLEL")) parallel = std::strtoul(e, nullptr, 10) != 0;
-        if (parallel) {
-            copt.separate_segments = true;
-            if (!std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = 8192;
-        }
+        // Programs above the segment size compile as a CHAIN of kernels, one translation unit each (codegen.hpp):
+        // the units compile concurrently on all host cores and nothing is linked.  MARAY_JIT_CHAIN=0 gives round
+        // 1's form (segment functions in one unit) for A/B.  sin/exp/ln stay out of line above the threshold:
+        // inlined, the code of a transcendental-heavy program is several MB of instructions no warp ever re-uses
+        // and the kernel becomes instruction-fetch bound (measured: 33.8 ms inlined vs 18.7 ms out of line on the
+        // 20 000-value deep scene, no_instruction stalls 9.1 per issued instruction; profiles/).
+        if (const char* e = std::getenv("MARAY_JIT_CHAIN")) copt.chain = std::strtoul(e, nullptr, 10) != 0;
+        if (copt.chain && !std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = 6144;
         h->modules = generate_cuda_modules(h->prog, copt, &info);
-        h->jit_link_maxreg = info.max_registers;
+        h->jit_chain = info.chain;
+        h->jit_frame_slots = info.frame_slots;
         if (h->modules.size() > 1) {
             CodegenInfo unused;
             h->source = generate_cuda_source(h->prog, copt, &unused);   // the same statements as ONE unit (tooling, tests)
@@ -925,7 +871,8 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         int rc = nvrtc_compile(h);
         h->stats.nvrtc_ms = now_ms() - t2;
         if (rc) return rc;
-        h->stats.jit_cubin_bytes = uint32_t(h->cubin.size());
+        h->stats.jit_cubin_bytes = 0;
+        for (const std::vector<char>& c : h->cubins) h->stats.jit_cubin_bytes += uint32_t(c.size());
     } else {
         // Row-uniform form by default; the all-wide form when the scalar file would crowd out the slot file
         // (or MARAY_INTERP_UNIFORM=0, for A/B).
@@ -934,7 +881,8 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         if (!compile_bytecode(h->prog, &h->bc, &err, uniform)) return fail(h, MARAY_E_COMPILE, err);
         if (uniform && h->bc.n_uniform > 4096 && !compile_bytecode(h->prog, &h->bc, &err, false)) return fail(h, MARAY_E_COMPILE, err);
         choose_interp_shape(h);
-        if (const char* e = std::getenv("MARAY_INTERP_DISPATCH")) h->interp_tree = std::string(e) == "tree";
+        h->interp_dispatch = 0;
+        if (const char* e = std::getenv("MARAY_INTERP_DISPATCH")) h->interp_dispatch = std::string(e) == "tree" ? 1 : (std::string(e) == "private" ? 2 : 0);
         if (!h->interp_block)
             return fail(h, MARAY_E_UNSUPPORTED, "program needs " + std::to_string(h->bc.n_wide) +
                                                     " live values per pixel, more than the interpreter's shared-memory slot file holds");
@@ -957,14 +905,22 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         for (Gpu& g : h->gpus) {
             CU_TRY(h, cudaSetDevice(g.device));
             if (backend == MARAY_BACKEND_NVRTC) {
-                CU_TRY(h, cudaLibraryLoadData(&g.lib, h->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-                CU_TRY(h, cudaLibraryGetKernel(&g.jit_kernel, g.lib, kJitKernelName));
-                cudaFuncAttributes fa;
-                if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(g.jit_kernel)) == cudaSuccess) h->stats.jit_registers = uint32_t(fa.numRegs);
-                else cudaGetLastError();
+                h->stats.jit_registers = 0;
+                for (const std::vector<char>& cubin : h->cubins) {
+                    cudaLibrary_t lib = nullptr;
+                    cudaKernel_t kern = nullptr;
+                    CU_TRY(h, cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+                    g.libs.push_back(lib);
+                    CU_TRY(h, cudaLibraryGetKernel(&kern, lib, kJitKernelName));
+                    g.jit_kernels.push_back(kern);
+                    cudaFuncAttributes fa;
+                    if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(kern)) == cudaSuccess)
+                        h->stats.jit_registers = std::max(h->stats.jit_registers, uint32_t(fa.numRegs));
+                    else cudaGetLastError();
+                }
                 if (h->jit_ncol || h->jit_nrow) {
-                    CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_x, g.lib, kJitPreXName));
-                    CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_y, g.lib, kJitPreYName));
+                    CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_x, g.libs[0], kJitPreXName));
+                    CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_y, g.libs[0], kJitPreYName));
                 }
             } else {
                 CU_TRY(h, cudaMalloc(&g.d_code, h->bc_device.size() * sizeof(uint64_t)));
@@ -1057,6 +1013,18 @@ int maray_cuda_get_source(const maray_cuda_t* h, char* buf, size_t cap, size_t* 
     if (buf && cap) {
         size_t n = std::min(cap - 1, h->source.size());
         std::memcpy(buf, h->source.data(), n);
+        buf[n] = '\0';
+    }
+    return MARAY_OK;
+}
+
+int maray_cuda_get_module(const maray_cuda_t* h, uint32_t index, char* buf, size_t cap, size_t* len) {
+    if (!h || index >= h->modules.size()) return MARAY_E_INVALID;
+    const std::string& m = h->modules[index];
+    if (len) *len = m.size();
+    if (buf && cap) {
+        size_t n = std::min(cap - 1, m.size());
+        std::memcpy(buf, m.data(), n);
         buf[n] = '\0';
     }
     return MARAY_OK;

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cinttypes>
+#include <functional>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -215,8 +216,14 @@ std::vector<uint8_t> find_booleans(const Program& prog) {
     return kind;
 }
 
-// Common generator.  modules[0] always holds the kernel; with opt.separate_segments (and a segmented
-// program) every segment function is its own translation unit in modules[1..].
+// Common generator.  Three forms:
+//   * one kernel (programs up to opt.segment_values values);
+//   * larger programs, opt.chain: one KERNEL per segment, each its own translation unit (modules[s]); values
+//     that cross a cut travel through a frame in global memory, F[slot * FS + pixel] (slot-major, so a warp's
+//     accesses are coalesced).  The units share nothing, so NVRTC compiles them concurrently and nothing is
+//     linked, no segment pays a call ABI, and every kernel has the whole register file;
+//   * larger programs, !opt.chain: __noinline__ segment functions inside ONE unit with a per-thread frame in
+//     local memory (round 1's form; kept for A/B).
 std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt, CodegenInfo* info) {
     // The per-pixel kernel evaluates the values that depend on both x and y; x-only / y-only frontier
     // values are loaded from the column / row tables (each at its first use), the x-only / y-only
@@ -251,24 +258,61 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         order_batch = prog.batch.size() == prog.order.size() ? prog.batch : std::vector<uint32_t>(prog.order.size(), 0);
     }
     uint64_t n_trans = prog.stats.op_count[OP_SIN] + prog.stats.op_count[OP_EXP] + prog.stats.op_count[OP_LN];
-    // __constant__ table of the scene's constants (64 KiB bank: at most 8000 entries; the rest
-    // stay literals).  Stored as bit patterns so NaN/infinity need no special spelling.
-    std::vector<int32_t> bank_index(prog.nodes.size(), -1);
-    std::vector<uint64_t> bank;
-    if (opt.constants_in_bank) {
-        for (size_t i = 0; i < prog.nodes.size() && bank.size() < 8000; i++) {
-            if (prog.nodes[i].op != OP_CONST) continue;
+
+    const uint32_t seg_len = opt.segment_values ? opt.segment_values : 4096;
+    const bool segmented = order.size() > seg_len;
+    const bool chain = segmented && opt.chain && !hoist;
+    // chain: cut into equal parts (the last kernel is not a stub)
+    const uint32_t n_seg = segmented ? uint32_t((order.size() + seg_len - 1) / seg_len) : 1;
+    const uint32_t seg_size = segmented ? uint32_t((order.size() + n_seg - 1) / n_seg) : uint32_t(order.size());
+    auto seg_lo = [&](uint32_t s) { return std::min(order.size(), size_t(s) * (chain ? seg_size : seg_len)); };
+    auto seg_hi = [&](uint32_t s) { return std::min(order.size(), size_t(s + 1) * (chain ? seg_size : seg_len)); };
+
+    // __constant__ table of the constants a translation unit uses (64 KiB bank: at most 8000 entries; the
+    // rest stay literals).  Stored as bit patterns so NaN/infinity need no special spelling.
+    struct Bank { std::vector<int32_t> index; std::vector<uint64_t> bits; };
+    auto make_bank = [&](size_t lo, size_t hi, bool everything) {
+        Bank bk;
+        bk.index.assign(prog.nodes.size(), -1);
+        if (!opt.constants_in_bank) return bk;
+        auto want = [&](uint32_t id) {
+            if (prog.nodes[id].op != OP_CONST || bk.index[id] >= 0 || bk.bits.size() >= 8000) return;
             // Small integers and halves stay literals: the compiler folds them exactly (x*1, 0+x as
             // a select, compares against 0) and encodes them as 32-bit immediates.
-            double kv = prog.nodes[i].k;
-            if (kv == kv && std::fabs(kv) <= 256.0 && kv * 2.0 == std::floor(kv * 2.0)) continue;
+            double kv = prog.nodes[id].k;
+            if (kv == kv && std::fabs(kv) <= 256.0 && kv * 2.0 == std::floor(kv * 2.0)) return;
             uint64_t bits;
-            std::memcpy(&bits, &prog.nodes[i].k, 8);
-            bank_index[i] = int32_t(bank.size());
-            bank.push_back(bits);
+            std::memcpy(&bits, &prog.nodes[id].k, 8);
+            bk.index[id] = int32_t(bk.bits.size());
+            bk.bits.push_back(bits);
+        };
+        if (everything) {
+            for (size_t i = 0; i < prog.nodes.size(); i++) want(uint32_t(i));
+        } else {
+            for (size_t i = lo; i < hi; i++) {
+                const Node& n = prog.nodes[order[i]];
+                if (op_is_unary(n.op) || op_is_binary(n.op)) want(n.a);
+                if (op_is_binary(n.op)) want(n.b);
+            }
+            for (int c = 0; c < 3; c++) want(prog.root[c]);
         }
-    }
-    Emitter em{prog, n_trans < opt.inline_transcendentals_below, opt.constants_in_bank ? &bank_index : nullptr};
+        return bk;
+    };
+    auto bank_text = [&](const Bank& bk) {
+        std::string t;
+        if (bk.bits.empty()) return t;
+        t += "__constant__ unsigned long long MRK_BITS[" + std::to_string(bk.bits.size()) + "] = {\n";
+        char kb[32];
+        for (size_t i = 0; i < bk.bits.size(); i++) {
+            std::snprintf(kb, sizeof kb, "0x%016" PRIx64 "ULL,%s", bk.bits[i], (i % 4 == 3) ? "\n" : " ");
+            t += kb;
+        }
+        t += "};\n#define MRK(i) (reinterpret_cast<const double*>(MRK_BITS)[i])\n";
+        return t;
+    };
+    const Bank whole_bank = make_bank(0, 0, true);
+
+    Emitter em{prog, n_trans < opt.inline_transcendentals_below, opt.constants_in_bank ? &whole_bank.index : nullptr};
     const std::vector<uint8_t> booleans = opt.boolean_logic ? find_booleans(prog) : std::vector<uint8_t>();
     if (opt.boolean_logic) em.boolean = &booleans;
     // The NOT form `1 + -(b)` reads b itself, not only its two operands: b must be visible wherever the
@@ -282,18 +326,13 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
     Emitter em_pre = em;                       // prologue kernels compute hoisted values, never load them
     if (hoist) { em.load_kind = &load_kind; em.table_index = &table_index; }
 
-    const uint32_t seg_len = opt.segment_values ? opt.segment_values : 4096;
-    const bool segmented = order.size() > seg_len;
-    const uint32_t n_seg = segmented ? uint32_t((order.size() + seg_len - 1) / seg_len) : 1;
-
-    const bool split = opt.separate_segments && segmented;
     const uint32_t block = opt.block ? ((opt.block + 31) / 32) * 32 : 256;
     const bool use_batches = !em.inline_trans;
     const bool scratch = use_batches && opt.scratch_batches;
     em.scratch_batches = scratch;
     std::string prelude = "// generated by maray_b200 (NVRTC back end); compiled with --fmad=false\n";
     // one private instance of the batch helpers per segment function of a single-unit program
-    const bool private_helpers = scratch && segmented && !split && opt.private_batch_helpers;
+    const bool private_helpers = scratch && segmented && !chain && opt.private_batch_helpers;
     if (scratch) {
         if (private_helpers) prelude += "#define MR_NO_DEFAULT_BATCH_HELPERS 1\n";
         prelude += "#define MR_SCR_STRIDE " + std::to_string(block) + "\n";
@@ -301,31 +340,48 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
     }
     prelude += kDeviceSemText;
     prelude += "\n";
-    std::string src;
-    src.reserve(order.size() * 40 + 8192);
-    src += prelude;
-    std::string bank_extern;   // what a separately compiled segment needs to see of the constant table
-    if (!bank.empty()) {
-        src += "__constant__ unsigned long long MRK_BITS[" + std::to_string(bank.size()) + "] = {\n";
-        char kb[32];
-        for (size_t i = 0; i < bank.size(); i++) {
-            std::snprintf(kb, sizeof kb, "0x%016" PRIx64 "ULL,%s", bank[i], (i % 4 == 3) ? "\n" : " ");
-            src += kb;
+
+    char buf[320];
+    auto kernel_head = [&](std::string& out, const char* extra_args) {
+        if (opt.min_blocks_per_sm)
+            std::snprintf(buf, sizeof buf, "extern \"C\" __global__ void __launch_bounds__(%u, %u) %s(const MrParams p%s) {\n",
+                          block, opt.min_blocks_per_sm, kJitKernelName, extra_args);
+        else
+            std::snprintf(buf, sizeof buf, "extern \"C\" __global__ void __launch_bounds__(%u) %s(const MrParams p%s) {\n",
+                          block, kJitKernelName, extra_args);
+        out += buf;
+        out += "  __shared__ unsigned int stage[3 * " + std::to_string(block) + " / 4];\n  (void)stage;\n";
+        out += "  const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;\n";
+        out += "  const bool active = j < p.n;\n";
+        out += "  const unsigned int pix = p.p0 + (active ? j : 0u);\n";   // idle lanes redo pixel p0
+        out += "  const unsigned int yi = pix / p.W;\n";
+        out += "  const unsigned int xi = pix - yi * p.W;\n";
+        out += "  const double X = (double)xi;\n  const double Y = (double)yi;\n";   // `x as f64`
+        out += "  const MrTexture* __restrict__ T = p.tex;\n  (void)T;\n";
+    };
+    auto store_call = [&](std::string& out, const std::vector<int32_t>& slot, const std::function<std::string(int32_t)>& frame_ref,
+                          const Emitter& e, const std::vector<uint8_t>* in_scope) {
+        out += "  mr_store_block(p, stage, ";
+        for (int c = 0; c < 3; c++) {
+            uint32_t r = prog.root[c];
+            if (slot[r] >= 0 && !(in_scope && (*in_scope)[r])) out += frame_ref(slot[r]);
+            else e.operand(out, r);
+            out += ", ";
         }
-        src += "};\n#define MRK(i) (reinterpret_cast<const double*>(MRK_BITS)[i])\n";
-        bank_extern = "extern __constant__ unsigned long long MRK_BITS[" + std::to_string(bank.size()) +
-                      "];\n#define MRK(i) (reinterpret_cast<const double*>(MRK_BITS)[i])\n";
-    }
-    std::vector<std::string> modules;   // modules[0] is filled in at the end
-    modules.emplace_back();
-    char buf[256];
+        out += "active, j);\n}\n";
+    };
+
+    std::vector<std::string> modules;
     uint32_t frame_slots = 0;
     std::vector<int32_t> slot(prog.nodes.size(), -1);
+    std::vector<uint32_t> seg_of(prog.nodes.size(), 0), last_use(prog.nodes.size(), 0);
 
     if (segmented) {
-        // Segment of each value, and the last segment that reads it (roots are read by the epilogue).
-        std::vector<uint32_t> seg_of(prog.nodes.size(), 0), last_use(prog.nodes.size(), 0);
-        for (size_t i = 0; i < order.size(); i++) seg_of[order[i]] = uint32_t(i / seg_len);
+        // Segment of each value, and the last segment that reads it.  The channels are read by the epilogue:
+        // after the last segment function (one unit), inside the last kernel (chain).
+        const uint32_t epilogue = chain ? n_seg - 1 : n_seg;
+        for (uint32_t s = 0; s < n_seg; s++)
+            for (size_t i = seg_lo(s); i < seg_hi(s); i++) seg_of[order[i]] = s;
         for (size_t i = 0; i < order.size(); i++) {
             const Node& n = prog.nodes[order[i]];
             uint32_t s = seg_of[order[i]];
@@ -340,7 +396,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         }
         for (int c = 0; c < 3; c++) {
             Op o = prog.nodes[prog.root[c]].op;
-            if (o != OP_CONST && o != OP_X && o != OP_Y) last_use[prog.root[c]] = n_seg;   // epilogue
+            if (o != OP_CONST && o != OP_X && o != OP_Y) last_use[prog.root[c]] = std::max(last_use[prog.root[c]], epilogue);
         }
         // Frame slots: a value gets one when it is read after its own segment; slots are recycled
         // once the last reading segment has finished.
@@ -348,8 +404,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         std::vector<int32_t> free_list;
         for (uint32_t s = 0; s < n_seg; s++) {
             if (s > 0) for (int32_t f : free_after[s - 1]) free_list.push_back(f);
-            size_t lo = size_t(s) * seg_len, hi = std::min(order.size(), lo + seg_len);
-            for (size_t i = lo; i < hi; i++) {
+            for (size_t i = seg_lo(s); i < seg_hi(s); i++) {
                 uint32_t id = order[i];
                 Op o = prog.nodes[id].op;
                 if (o == OP_X || o == OP_Y) continue;
@@ -362,23 +417,88 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
                 }
             }
         }
+    }
+    // values a segment reads from earlier segments
+    auto imports_of = [&](uint32_t s, bool with_roots) {
+        std::vector<uint32_t> tmp;
+        auto use = [&](uint32_t id) {
+            Op o = prog.nodes[id].op;
+            if (o == OP_CONST || o == OP_X || o == OP_Y) return;
+            if (seg_of[id] < s) tmp.push_back(id);
+        };
+        for (size_t i = seg_lo(s); i < seg_hi(s); i++) {
+            const Node& n = prog.nodes[order[i]];
+            if (op_is_unary(n.op) || op_is_binary(n.op)) use(n.a);
+            if (op_is_binary(n.op)) use(n.b);
+            if (uint32_t extra = not_operand(order[i]); extra != UINT32_MAX) use(extra);
+        }
+        if (with_roots) for (int c = 0; c < 3; c++) use(prog.root[c]);
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        return tmp;
+    };
+    // the statements of order[lo, hi) with the frame stores of values that outlive the segment
+    auto emit_range = [&](std::string& out, const Emitter& e, size_t lo, size_t hi, const std::function<std::string(int32_t)>& frame_ref,
+                          const char* store_guard) {
+        for (size_t i = lo; i < hi;) {
+            size_t j = i + 1;
+            if (use_batches && order_batch[i]) while (j < hi && order_batch[j] == order_batch[i]) j++;
+            if (j - i > 1) e.batch_calls(out, order, i, j);
+            else e.statement(out, order[i]);
+            for (size_t m = i; m < j; m++) {
+                uint32_t id = order[m];
+                if (opt.sync_every && (m - lo) % opt.sync_every == opt.sync_every - 1) out += "  __syncthreads();\n";
+                if (segmented && slot[id] >= 0) {
+                    std::snprintf(buf, sizeof buf, "  %s%s = v%u;\n", store_guard, frame_ref(slot[id]).c_str(), id);
+                    out += buf;
+                }
+            }
+            i = j;
+        }
+    };
 
+    if (chain) {
+        // ---- one kernel per segment ------------------------------------------------------------------
+        auto gref = [](int32_t f) { return "F[" + std::to_string(f) + "ull * FS + jj]"; };
         for (uint32_t s = 0; s < n_seg; s++) {
-            size_t lo = size_t(s) * seg_len, hi = std::min(order.size(), lo + seg_len);
-            static const char* const kSegArgs =
-                "(double* __restrict__ F, const double X, const double Y, const MrTexture* __restrict__ T, "
-                "const double* __restrict__ CV, const unsigned int CW, const double* __restrict__ RV, const unsigned int RW)";
-            std::string seg_text;
-            std::string& out = split ? seg_text : src;
-            if (split) {
-                // declaration for the kernel's translation unit; the definition gets its own
-                std::snprintf(buf, sizeof buf, "extern __device__ void mr_seg%u", s);
-                src += buf; src += kSegArgs; src += ";\n";
-                seg_text.reserve((hi - lo) * 48 + prelude.size() + 1024);
-                seg_text += prelude;
-                seg_text += bank_extern;
-                std::snprintf(buf, sizeof buf, "__device__ void mr_seg%u", s);
-            } else {
+            const Bank bk = make_bank(seg_lo(s), seg_hi(s), false);
+            Emitter e = em;
+            e.bank_index = opt.constants_in_bank ? &bk.index : nullptr;
+            e.helper_suffix.clear();
+            std::string unit;
+            unit.reserve((seg_hi(s) - seg_lo(s)) * 56 + prelude.size() + 4096);
+            unit += prelude;
+            unit += bank_text(bk);
+            std::snprintf(buf, sizeof buf, "// segment %u of %u\n", s, n_seg);
+            unit += buf;
+            kernel_head(unit, ", double* __restrict__ F, const unsigned long long FS");
+            unit += "  const unsigned long long jj = active ? j : 0ull;\n";       // idle lanes read pixel 0's frame column, write nothing
+            const bool last = s + 1 == n_seg;
+            std::vector<uint8_t> in_scope(prog.nodes.size(), 0);
+            for (uint32_t id : imports_of(s, last)) {
+                std::snprintf(buf, sizeof buf, "  const double v%u = %s;\n", id, gref(slot[id]).c_str());
+                unit += buf;
+                e.bool_from_double(unit, id);
+                in_scope[id] = 1;
+            }
+            for (size_t i = seg_lo(s); i < seg_hi(s); i++) in_scope[order[i]] = 1;
+            emit_range(unit, e, seg_lo(s), seg_hi(s), gref, "if (active) ");
+            if (last) store_call(unit, slot, gref, e, &in_scope);
+            else unit += "}\n";
+            modules.push_back(std::move(unit));
+        }
+    } else {
+        // ---- one translation unit ------------------------------------------------------------------------
+        std::string src;
+        src.reserve(order.size() * 40 + 8192);
+        src += prelude;
+        src += bank_text(whole_bank);
+        auto lref = [](int32_t f) { return "F[" + std::to_string(f) + "]"; };
+        if (segmented) {
+            for (uint32_t s = 0; s < n_seg; s++) {
+                static const char* const kSegArgs =
+                    "(double* __restrict__ F, const double X, const double Y, const MrTexture* __restrict__ T, "
+                    "const double* __restrict__ CV, const unsigned int CW, const double* __restrict__ RV, const unsigned int RW)";
                 if (private_helpers) {
                     std::snprintf(buf, sizeof buf, "MR_BATCH_HELPERS(_s%u)\n", s);
                     src += buf;
@@ -386,151 +506,77 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
                     em.helper_suffix = buf;
                 }
                 std::snprintf(buf, sizeof buf, "__device__ __noinline__ void mr_seg%u", s);
-            }
-            out += buf; out += kSegArgs; out += " {\n";
-            // imports: values defined in earlier segments and read here
-            std::vector<uint32_t> imports;
-            {
-                std::vector<uint32_t> tmp;
-                for (size_t i = lo; i < hi; i++) {
-                    const Node& n = prog.nodes[order[i]];
-                    auto use = [&](uint32_t id) {
-                        Op o = prog.nodes[id].op;
-                        if (o == OP_CONST || o == OP_X || o == OP_Y) return;
-                        if (seg_of[id] < s) tmp.push_back(id);
-                    };
-                    if (op_is_unary(n.op) || op_is_binary(n.op)) use(n.a);
-                    if (op_is_binary(n.op)) use(n.b);
-                    if (uint32_t extra = not_operand(order[i]); extra != UINT32_MAX) use(extra);
+                src += buf; src += kSegArgs; src += " {\n";
+                for (uint32_t id : imports_of(s, false)) {
+                    std::snprintf(buf, sizeof buf, "  const double v%u = F[%d];\n", id, slot[id]);
+                    src += buf;
+                    em.bool_from_double(src, id);
                 }
-                std::sort(tmp.begin(), tmp.end());
-                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-                imports.swap(tmp);
+                emit_range(src, em, seg_lo(s), seg_hi(s), lref, "");
+                src += "}\n";
             }
-            for (uint32_t id : imports) {
-                std::snprintf(buf, sizeof buf, "  const double v%u = F[%d];\n", id, slot[id]);
-                out += buf;
-                em.bool_from_double(out, id);
+        }
+        kernel_head(src, "");
+        src += "  const double* __restrict__ CV = p.colv + xi;\n  const unsigned int CW = p.W;\n";
+        src += "  const double* __restrict__ RV = p.rowv + (yi - p.row_base);\n  const unsigned int RW = p.rows;\n";
+        src += "  (void)CV; (void)CW; (void)RV; (void)RW;\n";
+        if (segmented) {
+            std::snprintf(buf, sizeof buf, "  double F[%u];\n", frame_slots ? frame_slots : 1);
+            src += buf;
+            for (uint32_t s = 0; s < n_seg; s++) {
+                std::snprintf(buf, sizeof buf, "  mr_seg%u(F, X, Y, T, CV, CW, RV, RW);\n", s);
+                src += buf;
             }
-            for (size_t i = lo; i < hi;) {
-                size_t j = i + 1;
-                if (use_batches && order_batch[i]) while (j < hi && order_batch[j] == order_batch[i]) j++;
-                if (j - i > 1) em.batch_calls(out, order, i, j);
-                else em.statement(out, order[i]);
-                for (size_t m = i; m < j; m++) {
-                    uint32_t id = order[m];
-                    if (opt.sync_every && (m - lo) % opt.sync_every == opt.sync_every - 1) out += "  __syncthreads();\n";
-                    if (slot[id] >= 0) {
-                        std::snprintf(buf, sizeof buf, "  F[%d] = v%u;\n", slot[id], id);
-                        out += buf;
+        } else {
+            emit_range(src, em, 0, order.size(), lref, "");
+        }
+        store_call(src, slot, lref, em, nullptr);
+
+        // Prologue kernels: one thread per column / per row evaluates the x-only / y-only sub-program and
+        // stores its frontier values (k-major, so the per-pixel kernel's column loads are coalesced and
+        // its row loads are a broadcast).
+        if (hoist) {
+            for (int which = 1; which <= 2; which++) {
+                const bool colk = which == 1;
+                src += colk ? "extern \"C\" __global__ void maray_pre_x(double* __restrict__ tab, const unsigned int n, const unsigned int base, const MrTexture* __restrict__ T) {\n"
+                            : "extern \"C\" __global__ void maray_pre_y(double* __restrict__ tab, const unsigned int n, const unsigned int base, const MrTexture* __restrict__ T) {\n";
+                src += "  const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;\n  if (t >= n) return;\n  (void)T;\n";
+                src += colk ? "  const double X = (double)(base + t);\n" : "  const double Y = (double)(base + t);\n";
+                // Values that depend on neither coordinate but are not literals either (a texture fetch at
+                // constant coordinates and what is computed from it) may feed the x-only / y-only cone: both
+                // prologues evaluate them too (there are at most a handful).
+                for (uint32_t id : prog.order) {
+                    const Node& n = prog.nodes[id];
+                    if (n.op == OP_X || n.op == OP_Y || (n.dep != (colk ? DEP_X : DEP_Y) && n.dep != DEP_CONST)) continue;
+                    em_pre.statement(src, id);
+                    if (load_kind[id] == which) {
+                        std::snprintf(buf, sizeof buf, "  tab[%uu * n + t] = v%u;\n", table_index[id], id);
+                        src += buf;
                     }
                 }
-                i = j;
+                src += "}\n";
             }
-            out += "}\n";
-            if (split) modules.push_back(std::move(seg_text));
         }
-    }
-
-    if (opt.min_blocks_per_sm)
-        std::snprintf(buf, sizeof buf, "extern \"C\" __global__ void __launch_bounds__(%u, %u) %s(const MrParams p) {\n",
-                      block, opt.min_blocks_per_sm, kJitKernelName);
-    else
-        std::snprintf(buf, sizeof buf, "extern \"C\" __global__ void __launch_bounds__(%u) %s(const MrParams p) {\n",
-                      block, kJitKernelName);
-    src += buf;
-    src += "  __shared__ unsigned int stage[3 * " + std::to_string(block) + " / 4];\n";
-    src += "  const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;\n";
-    src += "  const bool active = j < p.n;\n";
-    src += "  const unsigned int pix = p.p0 + (active ? j : 0u);\n";   // idle lanes redo pixel p0
-    src += "  const unsigned int yi = pix / p.W;\n";
-    src += "  const unsigned int xi = pix - yi * p.W;\n";
-    src += "  const double X = (double)xi;\n  const double Y = (double)yi;\n";   // `x as f64`
-    src += "  const MrTexture* __restrict__ T = p.tex;\n  (void)T;\n";
-    src += "  const double* __restrict__ CV = p.colv + xi;\n  const unsigned int CW = p.W;\n";
-    src += "  const double* __restrict__ RV = p.rowv + (yi - p.row_base);\n  const unsigned int RW = p.rows;\n";
-    src += "  (void)CV; (void)CW; (void)RV; (void)RW;\n";
-    if (segmented) {
-        std::snprintf(buf, sizeof buf, "  double F[%u];\n", frame_slots ? frame_slots : 1);
-        src += buf;
-        for (uint32_t s = 0; s < n_seg; s++) {
-            std::snprintf(buf, sizeof buf, "  mr_seg%u(F, X, Y, T, CV, CW, RV, RW);\n", s);
-            src += buf;
-        }
-    } else {
-        uint32_t since_sync = 0;
-        for (size_t i = 0; i < order.size();) {
-            size_t j = i + 1;
-            if (use_batches && order_batch[i]) while (j < order.size() && order_batch[j] == order_batch[i]) j++;
-            if (j - i > 1) em.batch_calls(src, order, i, j);
-            else em.statement(src, order[i]);
-            since_sync += uint32_t(j - i);
-            if (opt.sync_every && since_sync >= opt.sync_every) { src += "  __syncthreads();\n"; since_sync = 0; }
-            i = j;
-        }
-    }
-    src += "  mr_store_block(p, stage, ";
-    for (int c = 0; c < 3; c++) {
-        uint32_t r = prog.root[c];
-        if (segmented && slot[r] >= 0) {
-            std::snprintf(buf, sizeof buf, "F[%d]", slot[r]);
-            src += buf;
-        } else {
-            em.operand(src, r);
-        }
-        src += ", ";
-    }
-    src += "active, j);\n}\n";
-
-    // Prologue kernels: one thread per column / per row evaluates the x-only / y-only sub-program and
-    // stores its frontier values (k-major, so the per-pixel kernel's column loads are coalesced and
-    // its row loads are a broadcast).
-    if (hoist) {
-        for (int which = 1; which <= 2; which++) {
-            const bool colk = which == 1;
-            src += colk ? "extern \"C\" __global__ void maray_pre_x(double* __restrict__ tab, const unsigned int n, const unsigned int base, const MrTexture* __restrict__ T) {\n"
-                        : "extern \"C\" __global__ void maray_pre_y(double* __restrict__ tab, const unsigned int n, const unsigned int base, const MrTexture* __restrict__ T) {\n";
-            src += "  const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;\n  if (t >= n) return;\n  (void)T;\n";
-            src += colk ? "  const double X = (double)(base + t);\n" : "  const double Y = (double)(base + t);\n";
-            // Values that depend on neither coordinate but are not literals either (a texture fetch at
-            // constant coordinates and what is computed from it) may feed the x-only / y-only cone: both
-            // prologues evaluate them too (there are at most a handful).
-            for (uint32_t id : prog.order) {
-                const Node& n = prog.nodes[id];
-                if (n.op == OP_X || n.op == OP_Y || (n.dep != (colk ? DEP_X : DEP_Y) && n.dep != DEP_CONST)) continue;
-                em_pre.statement(src, id);
-                if (load_kind[id] == which) {
-                    std::snprintf(buf, sizeof buf, "  tab[%uu * n + t] = v%u;\n", table_index[id], id);
-                    src += buf;
-                }
-            }
-            src += "}\n";
-        }
+        modules.push_back(std::move(src));
     }
 
     if (info) {
         info->segments = n_seg;
+        info->chain = chain;
         info->frame_slots = segmented ? frame_slots : 0;
         info->transcendentals_inlined = em.inline_trans;
         info->block = block;
         info->n_col = hoist ? uint32_t(prog.col_values.size()) : 0;
         info->n_row = hoist ? uint32_t(prog.row_values.size()) : 0;
         info->dynamic_smem_bytes = scratch ? 2 * kScratchRows * block * uint32_t(sizeof(double)) : 0;   // argument rows + result rows
-        info->max_registers = 0;
-        if (opt.min_blocks_per_sm) {
-            uint32_t r = 65536u / (block * opt.min_blocks_per_sm);
-            r &= ~7u;                                   // register allocation granularity
-            info->max_registers = r > 255 ? 255 : r;
-        }
     }
-    modules[0] = std::move(src);
     return modules;
 }
 }  // namespace
 
 std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt, CodegenInfo* info) {
     CodegenOptions one = opt;
-    one.separate_segments = false;
+    one.chain = false;
     return generate(prog, one, info)[0];
 }
 

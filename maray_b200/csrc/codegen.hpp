@@ -11,9 +11,9 @@
 namespace maray {
 
 struct CodegenOptions {
-    // Programs with more values than this are cut into __noinline__ device functions of this many
-    // values each; values that cross a cut live in a per-thread frame (local memory).  Bounds
-    // ptxas time, which is super-linear in basic-block size.
+    // Programs with more values than this are cut into segments of at most this many values (see `chain`).
+    // Bounds ptxas time, which is super-linear in basic-block size, and sets how many units can compile
+    // concurrently.
     uint32_t segment_values = 16384;
     // sin/exp/ln are inlined below this many transcendental values, called out-of-line above it
     // (their inlined bodies dominate code size and compile time in transcendental-heavy scenes).
@@ -37,11 +37,11 @@ struct CodegenOptions {
     // pixel cost more issue slots and exposed latency than the 1 227 mostly one-instruction values
     // they replace.  Kept as MARAY_JIT_HOIST=1 for scenes with expensive x-only/y-only sub-programs.
     bool hoist = false;
-    // Emit every segment function as its own translation unit (generate_cuda_modules): the units are
-    // compiled concurrently with --relocatable-device-code and linked with nvJitLink.  This is what
-    // makes inlining sin/exp/ln affordable in transcendental-heavy programs (inlined bodies cost ~4x
-    // the compile time of out-of-line calls and run ~2x faster: no call ABI, no argument moves).
-    bool separate_segments = false;
+    // Programs above segment_values: one KERNEL per segment, each its own translation unit, values that cross
+    // a cut in a global-memory frame F[slot * FS + pixel].  The units share nothing: NVRTC compiles them
+    // concurrently, nothing is linked, no segment pays a call ABI.  false = __noinline__ segment functions in
+    // one unit with a per-thread local-memory frame (round 1's form, kept for A/B: MARAY_JIT_CHAIN=0).
+    bool chain = true;
     // Out-of-line sin/exp/ln batches pass arguments and results through per-thread rows of dynamic
     // shared memory to leaf helpers (device_libm.cuh, "scratch-batched form") instead of through the
     // call ABI's registers.  false = the register-argument x4/x2 helpers.
@@ -57,13 +57,11 @@ struct CodegenOptions {
 
 struct CodegenInfo {
     uint32_t segments = 0;
-    uint32_t frame_slots = 0;       // doubles of per-thread frame (0 when not segmented)
+    bool chain = false;             // one kernel per segment (modules.size() == segments), launched in order
+    uint32_t frame_slots = 0;       // doubles per pixel of the frame that carries values across cuts (0 when not segmented)
     bool transcendentals_inlined = true;
     uint32_t block = 256;           // threads per block the kernel must be launched with
     uint32_t n_col = 0, n_row = 0;  // doubles per column / per row in the hoisting tables (0 = no prologue)
-    // Register cap implied by __launch_bounds__(block, min_blocks): separately compiled segment
-    // functions do not see the kernel's launch bounds and must be given it as --maxrregcount.
-    uint32_t max_registers = 0;
     uint32_t dynamic_smem_bytes = 0; // dynamic shared memory the kernel must be launched with (batch scratch)
 };
 
@@ -74,8 +72,8 @@ constexpr const char* kJitPreYName = "maray_pre_y";
 
 // One translation unit (segment functions, if any, as __noinline__ functions of the same unit).
 std::string generate_cuda_source(const Program& prog, const CodegenOptions& opt, CodegenInfo* info);
-// modules[0] holds the kernel (and the scene's constant table); with opt.separate_segments and a
-// segmented program, modules[1..] hold one `mr_segK` device function each.
+// The translation units to compile: one, or -- opt.chain and a program above opt.segment_values -- one per
+// segment, each holding a kernel named kJitKernelName with the extra arguments (double* F, unsigned long long FS).
 std::vector<std::string> generate_cuda_modules(const Program& prog, const CodegenOptions& opt, CodegenInfo* info);
 
 }  // namespace maray

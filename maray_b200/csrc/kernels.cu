@@ -156,7 +156,9 @@ __device__ __forceinline__ void mr_un(const Files<P>& f, double (&acc)[P], doubl
     case BC_H_OUT + (C) * 4 + 2: { double x[P]; mr_fetch<P, 2>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break; \
     case BC_H_OUT + (C) * 4 + 3: { double x[P]; mr_fetch<P, 3>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break;
 
-template <int P, bool TREE>
+// DISPATCH: 0 = inline-PTX loop with one shared dispatch site, 1 = C++ switch only (A/B, debugging),
+// 2 = inline-PTX loop whose hottest bodies end in a dispatch of their own.
+template <int P, int DISPATCH>
 __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const uint64_t* __restrict__ code, unsigned int n_instr,
                                                     const double* __restrict__ consts, unsigned int n_consts, unsigned int n_scal,
                                                     unsigned int n_wide, unsigned int all_wide) {
@@ -220,10 +222,14 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
         for (;;) {
             // Inner loop (inline PTX, interp_dispatch.inc): fetch, indexed branch into a body specialised on
             // operation and operand kinds, store, next -- until an instruction it has no body for.
-            if constexpr (!TREE) {
+            if constexpr (DISPATCH == 0) {
                 if constexpr (P == 1) MR_INTERP_LOOP_P1(acc[0], sacc, pc, wbase_s, sbase_s, F.half_stride);
                 else if constexpr (P == 2) MR_INTERP_LOOP_P2(acc[0], acc[1], sacc, pc, wbase_s, sbase_s, F.half_stride);
                 else MR_INTERP_LOOP_P4(acc[0], acc[1], acc[2], acc[3], sacc, pc, wbase_s, sbase_s, F.half_stride);
+            } else if constexpr (DISPATCH == 2) {
+                if constexpr (P == 1) MR_INTERP_LOOPX_P1(acc[0], sacc, pc, wbase_s, sbase_s, F.half_stride);
+                else if constexpr (P == 2) MR_INTERP_LOOPX_P2(acc[0], acc[1], sacc, pc, wbase_s, sbase_s, F.half_stride);
+                else MR_INTERP_LOOPX_P4(acc[0], acc[1], acc[2], acc[3], sacc, pc, wbase_s, sbase_s, F.half_stride);
             }
             // One instruction through the C++ switch, which implements EVERY handler (with TREE: all of them).
             const uint64_t w = cs[(pc - cs_s) >> 3];
@@ -334,19 +340,19 @@ size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, uns
            (size_t)(n_wide + 3u) * pixels_per_thread * block * sizeof(double);   // + 3 channel-output slots
 }
 
-template <int P, bool TREE>
+template <int P, int DISPATCH>
 static cudaError_t launch_interp_as(const MrTileParams& p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
                                     unsigned int n_consts, unsigned int n_scal, unsigned int n_wide, bool all_wide,
                                     unsigned int block, unsigned int grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(maray_interp<P, TREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(maray_interp<P, DISPATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    maray_interp<P, TREE><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide ? 1u : 0u);
+    maray_interp<P, DISPATCH><<<grid, block, smem, stream>>>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide ? 1u : 0u);
     return cudaGetLastError();
 }
 
 cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
                           unsigned int n_consts, unsigned int n_uniform, unsigned int n_wide, bool all_wide, unsigned int block,
-                          unsigned int pixels_per_thread, cudaStream_t stream, bool tree_dispatch) {
+                          unsigned int pixels_per_thread, cudaStream_t stream, int dispatch) {
     if (p.rows == 0 || p.x1 <= p.x0) return cudaSuccess;
     const unsigned int n_scal = n_consts + n_uniform;
     const size_t smem = interp_smem_bytes(block, pixels_per_thread, n_wide, n_scal);
@@ -355,8 +361,9 @@ cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n
     if ((uint64_t)p.nxb * p.rows > 0x7fffffffull) return cudaErrorInvalidValue;
     const unsigned int grid = p.nxb * p.rows;
 #define MR_LAUNCH(PP)                                                                                                         \
-    (tree_dispatch ? launch_interp_as<PP, true>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream) \
-                   : launch_interp_as<PP, false>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream))
+    (dispatch == 1 ? launch_interp_as<PP, 1>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream) \
+     : dispatch == 2 ? launch_interp_as<PP, 2>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream) \
+                     : launch_interp_as<PP, 0>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream))
     switch (pixels_per_thread) {
     case 1: return MR_LAUNCH(1);
     case 2: return MR_LAUNCH(2);

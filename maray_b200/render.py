@@ -157,6 +157,18 @@ class CudaRenderer:
         self._check(self._L.maray_cuda_get_source(self._h, buf, n.value + 1, None))
         return buf.value.decode()
 
+    def modules(self) -> list:
+        """The translation units NVRTC compiled for the last scene (one, or one kernel per segment)."""
+        out = []
+        n = ctypes.c_size_t()
+        i = 0
+        while self._L.maray_cuda_get_module(self._h, i, None, 0, ctypes.byref(n)) == _lib.OK:
+            buf = ctypes.create_string_buffer(n.value + 1)
+            self._check(self._L.maray_cuda_get_module(self._h, i, buf, n.value + 1, None))
+            out.append(buf.value.decode())
+            i += 1
+        return out
+
     def bytecode(self):
         ni, nk = ctypes.c_size_t(), ctypes.c_size_t()
         self._check(self._L.maray_cuda_get_bytecode(self._h, None, 0, ctypes.byref(ni), None, 0, ctypes.byref(nk)))

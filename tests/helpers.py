@@ -100,6 +100,25 @@ extern "C" void host_run(unsigned char* out, double* f64_out, unsigned long long
 """
 
 
+# Chain form (one kernel per segment, values crossing a cut in a global frame F[slot * FS + pixel]): each
+# translation unit becomes its own shared object; they run in order over one frame buffer.
+HOST_DRIVER_CHAIN = r"""
+extern "C" void host_run(unsigned char* out, double* f64_out, unsigned long long plane, const MrTexture* tex,
+                         unsigned int p0, unsigned int n, unsigned int W, double* F, unsigned long long FS) {
+    MrParams p;
+    p.out = out; p.f64_out = f64_out; p.f64_plane = plane; p.tex = tex; p.p0 = p0; p.n = n; p.W = W;
+    p.out_aligned = 0; p.colv = nullptr; p.rowv = nullptr; p.row_base = 0; p.rows = 0;
+    blockDim.x = 256; blockDim.y = blockDim.z = 1;
+    unsigned int blocks = (n + 255) / 256;
+    for (unsigned int b = 0; b < blocks; b++) {
+        blockIdx.x = b;
+        for (int pass = 0; pass < 2; pass++)          // see HOST_DRIVER: second pass = after the barrier
+            for (unsigned int t = 0; t < 256; t++) { threadIdx.x = t; maray_jit(p, F, FS); }
+    }
+}
+"""
+
+
 class _Tex(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("w", ctypes.c_uint32), ("h", ctypes.c_uint32)]
 
@@ -142,6 +161,39 @@ def host_jit_run(source: str, w: int, p0: int, n: int, textures=(), perturb_libm
     colv = np.zeros(4096 * w, dtype=np.float64)
     rowv = np.zeros(4096 * rows, dtype=np.float64)
     lib.host_run(rgb.ctypes.data, planes.ctypes.data, n, ctypes.addressof(tab), p0, n, w, colv.ctypes.data, rowv.ctypes.data)
+    return rgb, planes
+
+
+def host_chain_run(modules, w: int, p0: int, n: int, frame_slots: int, textures=()):
+    """Runs the chain form of a program (CudaRenderer.modules(): one kernel per segment) on the CPU: every unit
+    is compiled on its own and they run in order over one frame.  Returns (rgb uint8 (n,3), planes float64 (3,n))."""
+    rgb = np.zeros((n, 3), dtype=np.uint8)
+    planes = np.zeros((3, n), dtype=np.float64)
+    arrs = [np.ascontiguousarray(t, dtype=np.uint8) for t in textures]
+    tab = (_Tex * max(1, len(arrs)))()
+    for i, a in enumerate(arrs):
+        tab[i].data = a.ctypes.data
+        tab[i].w, tab[i].h = a.shape[1], a.shape[0]
+    fs = ((n + 255) // 256) * 256
+    frame = np.full(max(1, frame_slots) * fs, np.nan, dtype=np.float64)     # a read of a never-written slot shows up as NaN
+    for source in modules:
+        key = hashlib.sha256(source.encode()).hexdigest() + "chain"
+        lib = _CACHE.get(key)
+        if lib is None:
+            d = tempfile.mkdtemp(prefix="maray_hostjit_")
+            src = os.path.join(d, "k.cpp")
+            with open(src, "w") as f:
+                f.write(HOST_SHIM)
+                f.write(source.replace('extern "C" __global__', "static"))
+                f.write(HOST_DRIVER_CHAIN)
+            so = os.path.join(d, "k.so")
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                                   "-w", "-o", so, src])
+            lib = ctypes.CDLL(so)
+            lib.host_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p,
+                                     ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_ulonglong]
+            _CACHE[key] = lib
+        lib.host_run(rgb.ctypes.data, planes.ctypes.data, n, ctypes.addressof(tab), p0, n, w, frame.ctypes.data, fs)
     return rgb, planes
 
 

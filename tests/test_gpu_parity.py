@@ -220,29 +220,34 @@ def _heavy_scene_with_out_of_range_arguments(w, h):
     return E.to_bytes([w, h], out)
 
 
-@pytest.mark.parametrize("form", ["scratch", "registers", "separate_units"])
+@pytest.mark.parametrize("form", ["scratch", "registers", "chain", "functions"])
 def test_batched_transcendentals_and_their_repair_path(monkeypatch, form):
     """The out-of-line sin/exp/ln forms of the NVRTC back end on a program above the batching threshold,
-    with arguments that must take the libdevice repair path.  All forms run the same device routines,
-    so their f64 planes must be bit-identical to each other; against the oracle the usual tolerance."""
+    with arguments that must take the libdevice repair path, and both ways of cutting a large program (a chain
+    of kernels over a global frame -- rendered in several chunks here --, segment functions in one unit).  All
+    forms run the same device routines, so their f64 planes must be bit-identical to each other; against the
+    oracle the usual tolerance."""
     w, h = 96, 64
     scene = _heavy_scene_with_out_of_range_arguments(w, h)
     want_rgb, want = OracleScene(scene).render_window(0, w, 0, h, want_f64=True)
     if form == "registers":
         monkeypatch.setenv("MARAY_JIT_SCRATCH", "0")
-    if form == "separate_units":
-        monkeypatch.setenv("MARAY_JIT_PARALLEL", "1")
-        monkeypatch.setenv("MARAY_JIT_SEGMENT_VALUES", "4096")
+    monkeypatch.setenv("MARAY_JIT_SEGMENT_VALUES", "3000" if form in ("chain", "functions") else "100000")
+    if form == "functions":
+        monkeypatch.setenv("MARAY_JIT_CHAIN", "0")
+    if form == "chain":
+        monkeypatch.setenv("MARAY_JIT_FRAME_MB", "1")        # 1 MiB of frame: the 96x64 image takes several chunks
     with _renderer(scene, "nvrtc") as r:
         st = r.stats()
         planes, rgb = r.render_window_f64(w, h, 0, w, 0, h)
         frame = r.render(w, h)
-    if form == "separate_units":
-        assert st["jit_units"] > 1 and st["link_ms"] > 0
+    if form == "chain":
+        assert st["jit_units"] == st["jit_segments"] >= 3
+    if form == "functions":
+        assert st["jit_units"] == 1 and st["jit_segments"] >= 3
     assert np.array_equal(frame, rgb)
-    monkeypatch.delenv("MARAY_JIT_SCRATCH", raising=False)
-    monkeypatch.delenv("MARAY_JIT_PARALLEL", raising=False)
-    monkeypatch.delenv("MARAY_JIT_SEGMENT_VALUES", raising=False)
+    for k in ("MARAY_JIT_SCRATCH", "MARAY_JIT_CHAIN", "MARAY_JIT_SEGMENT_VALUES", "MARAY_JIT_FRAME_MB"):
+        monkeypatch.delenv(k, raising=False)
     # yardstick: the interpreter kernel, whose handlers inline the scalar routines
     with _renderer(scene, "interp") as r:
         ref_planes, ref_rgb = r.render_window_f64(w, h, 0, w, 0, h)
@@ -407,7 +412,7 @@ def test_textured_scene_at_stated_size(backend):
 
 def test_deep_scene_at_stated_size_default_path():
     """Config 5 at its stated size: ~1e5 values, 8192x8192, through the DEFAULT form of the NVRTC back end
-    for a program of this size (segment functions with private batch helpers).  Small windows -- the
+    for a program of this size (a chain of segment kernels over a global frame).  Small windows -- the
     oracle's by-name Let lookup makes one pixel of this scene cost ~0.2 s of CPU -- spread over the frame,
     and size-independent properties of the full frame: bands reassemble it, windows equal it."""
     scene = scenes.deep()
@@ -415,7 +420,7 @@ def test_deep_scene_at_stated_size_default_path():
     oracle = OracleScene(scene)
     with _renderer(scene, "nvrtc") as r:
         st = r.stats()
-        assert st["dag_nodes"] > 90000 and st["jit_segments"] > 1
+        assert st["dag_nodes"] > 90000 and st["jit_segments"] > 1 and st["jit_units"] == st["jit_segments"]   # a chain of kernels
         windows = [(0, 0, 16, 8), (4088, 4090, 16, 8), (8176, 8184, 16, 8), (1000, 7000, 16, 8)]
         frame = _windows_and_rows_vs_oracle(r, oracle, w, h, windows, [], exact=False)
         import torch

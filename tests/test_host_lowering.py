@@ -11,7 +11,7 @@ from maray_b200 import CudaRenderer, scenes
 from maray_b200 import expr as E
 from oracle.oracle import OracleScene
 
-from helpers import as_u8, bits_equal, bytecode_run, host_jit_run
+from helpers import as_u8, bits_equal, bytecode_run, host_chain_run, host_jit_run
 
 
 def _oracle_window(scene, textures, x0, x1, y0, y1):
@@ -256,34 +256,41 @@ def test_hoisting_option_is_value_preserving(monkeypatch, chess_bytes):
             assert np.array_equal(rgb, want_rgb.reshape(w, 3))
 
 
-@pytest.mark.parametrize("form", ["scratch", "registers", "separate_units"])
+@pytest.mark.parametrize("form", ["scratch", "registers", "chain", "functions"])
 def test_transcendental_batching_keeps_values(monkeypatch, form):
     """Programs with >= 2048 sin/exp/ln values get their schedule batched and call out-of-line helpers:
-    through the per-thread shared-memory scratch (default), through register arguments (x4/x2), or --
-    MARAY_JIT_PARALLEL=1 -- with every segment function in its own translation unit (linked with
-    nvJitLink; the text checked here is the same statements as one unit)."""
+    through the per-thread shared-memory scratch (default) or through register arguments (x4/x2).  Above the
+    segment size a program is cut: into a CHAIN of kernels, one translation unit each, values crossing a cut
+    in a global frame (default), or into segment functions inside one unit (MARAY_JIT_CHAIN=0)."""
     if form == "registers":
         monkeypatch.setenv("MARAY_JIT_SCRATCH", "0")
-    if form == "separate_units":
-        monkeypatch.setenv("MARAY_JIT_PARALLEL", "1")
-        monkeypatch.setenv("MARAY_JIT_SEGMENT_VALUES", "4096")
-        monkeypatch.setenv("MARAY_JIT_CACHE", "off")          # the compile and link statistics below are those of a real compile
+    monkeypatch.setenv("MARAY_JIT_SEGMENT_VALUES", "3000" if form in ("chain", "functions") else "100000")
+    if form in ("chain", "functions"):
+        monkeypatch.setenv("MARAY_JIT_CACHE", "off")          # the compile statistics below are those of a real compile
+    if form == "functions":
+        monkeypatch.setenv("MARAY_JIT_CHAIN", "0")
     scene = scenes.deep(48, 32, n_values=9000, seed=3)
     with CudaRenderer(gpus=0) as r:
         r.load(scene)
         st = r.compile("nvrtc")
         src = r.source()
+        modules = r.modules()
         r.compile("interp")
         code, consts = r.bytecode()
     assert st["n_sin"] + st["n_exp"] + st["n_ln"] >= 2048
     body = src[src.index("mr_seg0") if "mr_seg0" in src else src.index('extern "C" __global__'):]
     assert ("_x4(" in body) if form == "registers" else ("_batch" in body and "MR_R(" in body)
-    if form == "separate_units":
-        assert st["jit_units"] == st["jit_segments"] + 1 and st["jit_segments"] >= 2 and st["jit_compile_threads"] >= 1
-        assert st["link_ms"] > 0 and st["jit_cubin_bytes"] > 1000
-    else:
-        assert st["jit_units"] == 1 and st["link_ms"] == 0
     want_rgb, want = _oracle_window(scene, [], 0, 48, 7, 8)
+    if form == "chain":
+        assert st["jit_segments"] >= 3 and st["jit_units"] == st["jit_segments"] == len(modules) and st["jit_compile_threads"] >= 1
+        assert st["jit_frame_slots"] > 0 and st["jit_cubin_bytes"] > 1000
+        assert all("double* __restrict__ F, const unsigned long long FS" in m for m in modules) and "mr_store_block" in modules[-1]
+        assert all("mr_store_block(p" not in m for m in modules[:-1])
+        rgb, planes = host_chain_run(modules, 48, 7 * 48, 48, st["jit_frame_slots"])
+        assert bits_equal(planes, want.reshape(3, 48)).all() and np.array_equal(rgb, want_rgb.reshape(48, 3))
+    else:
+        assert st["jit_units"] == 1 and len(modules) == 1 and modules[0] == src
+        assert (st["jit_segments"] >= 3) == (form == "functions")
     rgb, planes = host_jit_run(src, 48, 7 * 48, 48)
     assert bits_equal(planes, want.reshape(3, 48)).all() and np.array_equal(rgb, want_rgb.reshape(48, 3))
     bc = bytecode_run(code, consts, np.arange(48), np.full(48, 7))

@@ -34,7 +34,7 @@ BIN_OPS = ["add", "mul", "max", "min"]
 UN_OPS = {0: "neg", 1: "abs", 4: "step", 8: "mov"}          # u index -> op (others: C++ switch)
 
 
-def gen(P):
+def gen(P, PRIVATE_DISPATCH):
     """asm operands: %0..%(P-1) acc, %P sacc, %(P+1) pc (shared-window address of the instruction word to run
     next; on return: of the instruction the block has no body for), then wbase, sbase, hs (in)."""
     acc = [f"%{k}" for k in range(P)]
@@ -70,7 +70,18 @@ def gen(P):
         emit(f"add.u32 {pc}, {pc}, 8;")
         emit(f"ld.shared.v2.b32 {{lo, hi}}, [{pc}];")
 
-    def dispatch():
+    private_sites = []
+
+    def dispatch(private=False):
+        if private:
+            # a dispatch of its own, with its own copy of the table: the index arithmetic and the table load can
+            # then be scheduled early in the body, overlapping the body's own loads and arithmetic
+            k = len(private_sites)
+            private_sites.append(k)
+            emit("and.b32 t, lo, 511;")
+            emit(f"TBL{k}: .branchtargets @TARGETS@;")
+            emit(f"brx.idx t, TBL{k};")
+            return
         # ONE shared dispatch site.  (With an indexed branch at the end of every body ptxas expands each site
         # into its own 512-entry table of BRA instructions -- 1.5 MB of code, measured -- instead of the single
         # constant-bank table + LDC/BRX it builds for one site.)
@@ -119,7 +130,7 @@ def gen(P):
     xs = [f"x{k}" for k in range(P)]
     ys = [f"y{k}" for k in range(P)]
 
-    def body(label, kinds, store, shape, compute):
+    def body(label, kinds, store, shape, compute, hot=False):
         """One handler: addresses from the current word, next word, operand loads, arithmetic, store, dispatch."""
         emit(f"{label}:")
         srcs = []
@@ -148,7 +159,7 @@ def gen(P):
                 wide_store("add_")
             else:
                 emit(f"st.shared.f64 [add_], {sacc};")     # the same bits from every lane of the block
-        dispatch()
+        dispatch(private=hot and PRIVATE_DISPATCH)
 
     targets = ["GEN"] * 512          # everything without a body here, END (0) and YIELD (1) included, leaves the block
     emit("{")
@@ -179,7 +190,9 @@ def gen(P):
                         else:
                             for k in range(P):
                                 binop(op, acc[k], x[k], y[k])
-                    body(f"H{hid}{sfx}", [("a", ka, xs), ("b", kb, ys)], store, "wide", compute)
+                    body(f"H{hid}{sfx}", [("a", ka, xs), ("b", kb, ys)], store, "wide", compute,
+                         hot=(op in ("add", "mul") and (ka, kb) in ((A, S), (A, W), (S, A), (W, A), (W, S), (W, W), (S, W)))
+                             or (op in ("max", "min") and (ka, kb) in ((A, W), (W, A), (A, S), (S, A))))
         # wide unary
         for u, op in UN_OPS.items():
             for ka in range(4):
@@ -195,7 +208,7 @@ def gen(P):
                     else:
                         for k in range(P):
                             unop(op, acc[k], x[k])
-                body(f"H{hid}{sfx}", [("a", ka, xs)], store, "wide", compute)
+                body(f"H{hid}{sfx}", [("a", ka, xs)], store, "wide", compute, hot=(op in ("neg", "step") and ka == A))
         # scalar shape: binary (kinds S/T only: index = (ka == T) * 2 + (kb == T)), unary
         for oi, op in enumerate(BIN_OPS):
             for ta in range(2):
@@ -223,11 +236,12 @@ def gen(P):
 
 def main():
     out = ["// GENERATED by tools/gen_interp_dispatch.py -- do not edit; see that file for the why and the semantics.",
-           "// One macro per pixels-per-thread count: MR_INTERP_LOOP_P<P>(acc..., sacc, pc, wbase, sbase, hs)."]
-    for P in (1, 2, 4):
-        lines = gen(P)
+           "// One macro per pixels-per-thread count: MR_INTERP_LOOP_P<P>(acc..., sacc, pc, wbase, sbase, hs);",
+           "// MR_INTERP_LOOPX_P<P> is the variant whose hottest bodies end in a dispatch of their own."]
+    for P, private in ((1, False), (2, False), (4, False), (1, True), (2, True), (4, True)):
+        lines = gen(P, private)
         accs = ", ".join(f"ACC{k}" for k in range(P))
-        out.append(f"#define MR_INTERP_LOOP_P{P}({accs}, SACC, PC, WBASE, SBASE, HS) \\")
+        out.append(f"#define MR_INTERP_LOOP{'X' if private else ''}_P{P}({accs}, SACC, PC, WBASE, SBASE, HS) \\")
         out.append("    asm volatile( \\")
         for s in lines:
             out.append(f'        "{s}\\n" \\')

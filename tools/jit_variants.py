@@ -46,7 +46,7 @@ for var in variants:
         t0 = time.time()
         st = r.compile("nvrtc")
         rec = {"variant": var or "(default)", "compile_s": round(time.time() - t0, 2), "cache_hit": st["jit_cache_hit"],
-               "units": st["jit_units"], "threads": st["jit_compile_threads"], "link_s": round(st["link_ms"] / 1e3, 2),
+               "units": st["jit_units"], "threads": st["jit_compile_threads"],
                "segments": st["jit_segments"], "frame_slots": st["jit_frame_slots"], "regs": st["jit_registers"],
                "cubin_mb": round(st["jit_cubin_bytes"] / 1e6, 2)}
         if have_gpu:
