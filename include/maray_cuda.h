@@ -42,7 +42,11 @@ enum {
 /* Back ends (siblings of the reference's WAT code generator, reference src/wasm.rs). */
 enum {
     MARAY_BACKEND_INTERP = 0,  /* flat register bytecode run by the hand-written interpreter kernel */
-    MARAY_BACKEND_NVRTC = 1    /* straight-line CUDA compiled at run time for sm_100a, --fmad=false  */
+    MARAY_BACKEND_NVRTC = 1,   /* straight-line CUDA compiled at run time for sm_100a, --fmad=false  */
+    MARAY_BACKEND_AUTO = 2     /* time to first frame: cubins from the cache if they are there; otherwise the
+                                  interpreter renders at once while NVRTC compiles on another thread, and renders
+                                  switch to the generated kernels (between row chunks) when they are built.  Both
+                                  back ends produce the same bytes. */
 };
 
 /* Progress reporting, the counterpart of `Report` (reference src/report.rs:19-27).  The callback is
@@ -76,6 +80,9 @@ typedef struct maray_cuda_stats {
     uint32_t interp_uniform_slots;/* per-block row-uniform scalar slots (interpreter; 0 in the all-wide form) */
     uint32_t interp_block;        /* interpreter launch shape: threads per block ...                 */
     uint32_t interp_pixels_per_thread; /* ... and pixels per thread (a block spans block*ppt pixels of one row) */
+    uint32_t tier_rows_interp;    /* MARAY_BACKEND_AUTO, last render: rows the interpreter rendered before the
+                                     generated kernels took over (0 once they are installed)               */
+    uint32_t jit_active;          /* 1 when launches go to the generated kernels                           */
     /* timings, milliseconds */
     double lower_ms;              /* Expr -> SSA                                                     */
     double codegen_ms;            /* SSA -> source / bytecode                                        */

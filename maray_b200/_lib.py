@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmaray_cuda.so")
 
 OK, E_INVALID, E_PARSE, E_SCENE, E_COMPILE, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-BACKEND_INTERP, BACKEND_NVRTC = 0, 1
+BACKEND_INTERP, BACKEND_NVRTC, BACKEND_AUTO = 0, 1, 2
 REPORT_NONE, REPORT_ROW, REPORT_DURATION_MS = 0, 1, 2
 
 REPORT_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_uint32, ctypes.c_uint32,
@@ -26,7 +26,7 @@ class Stats(ctypes.Structure):
             "dag_depth", "legacy_layout", "backend", "interp_instructions", "interp_slots",
             "jit_segments", "jit_frame_slots", "jit_registers", "jit_source_bytes", "jit_cubin_bytes",
             "jit_units", "jit_compile_threads", "jit_cache_hit", "interp_uniform_slots", "interp_block",
-            "interp_pixels_per_thread")]
+            "interp_pixels_per_thread", "tier_rows_interp", "jit_active")]
         + [("lower_ms", ctypes.c_double), ("codegen_ms", ctypes.c_double), ("nvrtc_ms", ctypes.c_double),
            ("load_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double * 8), ("gather_ms", ctypes.c_double),
            ("d2h_ms", ctypes.c_double), ("render_ms", ctypes.c_double)]

@@ -74,6 +74,28 @@ struct Gpu {
 
 }  // namespace
 
+// What the NVRTC back end builds from a program.  It does not touch the handle or a device, so it can be
+// made on another thread while the interpreter renders (MARAY_BACKEND_AUTO).
+struct JitBuild {
+    std::vector<std::string> modules;         // every translation unit
+    std::string source;                       // the same statements as ONE unit (tooling, host-side tests)
+    std::vector<std::vector<char>> cubins;    // one per unit
+    CodegenInfo info;
+    unsigned maxreg = 0;
+    double codegen_ms = 0.0, nvrtc_ms = 0.0;
+    uint32_t registers = 0, compile_threads = 0, cache_hit = 0;
+    std::string error;
+};
+
+struct JitJob {
+    std::thread th;
+    std::atomic<int> state{0};                // 0 running, 1 built, 2 failed
+    std::atomic<bool> cancel{false};          // set by the handle when the result is no longer wanted
+    Program prog;                             // the job's own copy
+    JitBuild build;
+    int rc = 0;
+};
+
 struct maray_cuda {
     std::vector<Gpu> gpus;
     std::string error;
@@ -83,14 +105,15 @@ struct maray_cuda {
     bool textures_uploaded = false;
     Program prog;
     bool compiled = false;
-    int backend = -1;
-    std::string source;                 // the kernel's translation unit (== modules[0])
-    std::vector<std::string> modules;   // every translation unit of the last NVRTC compile
-    std::vector<std::vector<char>> cubins;   // one per translation unit
+    int backend = -1;                   // as asked for: MARAY_BACKEND_*
+    bool use_jit = false;               // launches go to the generated kernels (else: to the interpreter)
+    bool have_interp = false;           // bytecode compiled (and uploaded when there are GPUs)
+    std::unique_ptr<JitJob> job;        // MARAY_BACKEND_AUTO: the NVRTC build in flight, or finished and not yet installed
+    JitBuild jit;                       // the installed build
     Bytecode bc;
     std::vector<uint64_t> bc_device;                   // bc.code with operand fields scaled for the launch shape
     unsigned interp_block = 128, interp_ppt = 2;       // launch shape: threads per block, pixels per thread
-    int interp_dispatch = 0;                           // MARAY_INTERP_DISPATCH=tree|private (kernels.hpp launch_interp), A/B
+    int interp_dispatch = 0;                           // MARAY_INTERP_DISPATCH=tree (kernels.hpp launch_interp), A/B
     unsigned jit_block = 256;
     unsigned jit_dyn_smem = 0;                         // dynamic shared memory of the generated kernel
     unsigned jit_maxreg = 0;
@@ -111,6 +134,11 @@ int fail(maray_cuda* h, int code, const std::string& msg) {
     return code;
 }
 
+int jit_build(const Program& prog, JitBuild* jb, bool cached_only, const std::atomic<bool>* cancel);
+int jit_install(maray_cuda* h, JitBuild&& jb);
+int interp_build_and_install(maray_cuda* h);
+void fill_jit_stats(maray_cuda* h);
+
 #define CU_TRY(h, expr)                                                                                   \
     do {                                                                                                  \
         cudaError_t e_ = (expr);                                                                          \
@@ -119,7 +147,20 @@ int fail(maray_cuda* h, int code, const std::string& msg) {
                                              cudaGetErrorString(e_) + ")");                               \
     } while (0)
 
-void release_backend(maray_cuda* h) {
+// cancel: the result is no longer wanted (another scene, another back end) -- units not started yet are skipped,
+// a unit inside NVRTC runs to its end.  Without cancel (destroy) the build is left to finish, so that its cubins
+// reach the cache and the next process starts on the generated kernels.
+void stop_job(maray_cuda* h, bool cancel) {
+    if (!h->job) return;
+    if (cancel) h->job->cancel = true;
+    if (h->job->th.joinable()) h->job->th.join();
+    h->job.reset();
+}
+
+void release_backend(maray_cuda* h, bool cancel_job = true) {
+    stop_job(h, cancel_job);
+    h->use_jit = false;
+    h->have_interp = false;
     for (Gpu& g : h->gpus) {
         cudaSetDevice(g.device);
         for (cudaLibrary_t l : g.libs) cudaLibraryUnload(l);
@@ -309,8 +350,8 @@ std::string jit_cache_dir() {
     return dir;
 }
 
-int nvrtc_compile(maray_cuda* h) {
-    const size_t n_units = h->modules.size();
+int nvrtc_compile(JitBuild* jb, const std::atomic<bool>* cancel, bool cached_only) {
+    const size_t n_units = jb->modules.size();
     std::vector<std::string> options = {
         "--gpu-architecture=sm_100a",
         "--fmad=false",               // the reference never fuses a*b+c
@@ -322,16 +363,15 @@ int nvrtc_compile(maray_cuda* h) {
     bool lineinfo = true;
     if (const char* e = std::getenv("MARAY_JIT_LINEINFO")) lineinfo = std::strtoul(e, nullptr, 10) != 0;
     if (lineinfo) options.push_back("-lineinfo");
-    if (h->jit_maxreg) options.push_back("--maxrregcount=" + std::to_string(h->jit_maxreg));
+    if (jb->maxreg) options.push_back("--maxrregcount=" + std::to_string(jb->maxreg));
     if (std::getenv("MARAY_JIT_NOSLOW")) options.push_back("-DMR_NO_SLOW=1");   // experiment only (wrong for huge/NaN arguments)
     if (const char* e = std::getenv("MARAY_LIBM"))      // A/B: MARAY_LIBM=cuda uses libdevice's sin/exp/log
         if (std::string(e) == "cuda") options.push_back("-DMR_LIBM_PLAIN=1");
 
-    h->stats.jit_registers = 0;
-    h->stats.jit_units = uint32_t(n_units);
-    h->stats.jit_compile_threads = 0;
-    h->stats.jit_cache_hit = 0;
-    h->cubins.assign(n_units, {});
+    jb->registers = 0;
+    jb->compile_threads = 0;
+    jb->cache_hit = 0;
+    jb->cubins.assign(n_units, {});
 
     // cache: per unit, so an edit that changes one segment recompiles one segment
     const std::string cache_dir = jit_cache_dir();
@@ -340,29 +380,36 @@ int nvrtc_compile(maray_cuda* h) {
     for (size_t i = 0; i < n_units; i++) {
         uint32_t regs = 0;
         if (!cache_dir.empty()) {
-            cache_path[i] = cache_dir + "/" + cache_key(h->modules[i], options) + ".mrcubin";
-            if (cache_load(cache_path[i], &h->cubins[i], &regs)) {
-                h->stats.jit_registers = std::max(h->stats.jit_registers, regs);
+            cache_path[i] = cache_dir + "/" + cache_key(jb->modules[i], options) + ".mrcubin";
+            if (cache_load(cache_path[i], &jb->cubins[i], &regs)) {
+                jb->registers = std::max(jb->registers, regs);
                 continue;
             }
         }
         todo.push_back(i);
     }
-    if (todo.empty()) { h->stats.jit_cache_hit = 1; return MARAY_OK; }
+    if (todo.empty()) { jb->cache_hit = 1; return MARAY_OK; }
+    if (cached_only) { jb->error = "not every unit is in the cubin cache"; return MARAY_E_COMPILE; }
 
     std::vector<UnitResult> res(n_units);
     unsigned n_threads = std::thread::hardware_concurrency();
     if (const char* e = std::getenv("MARAY_JIT_THREADS")) n_threads = unsigned(std::strtoul(e, nullptr, 10));
     n_threads = std::max(1u, std::min<unsigned>(n_threads, unsigned(todo.size())));
-    h->stats.jit_compile_threads = n_threads;
+    jb->compile_threads = n_threads;
     if (n_threads == 1) {
-        for (size_t i : todo) compile_unit(h->modules[i], options, &res[i]);
+        for (size_t i : todo) {
+            if (cancel && *cancel) { jb->error = "compile cancelled"; return MARAY_E_COMPILE; }
+            compile_unit(jb->modules[i], options, &res[i]);
+        }
     } else {
         std::atomic<size_t> next{0};
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < n_threads; t++)
             pool.emplace_back([&] {
-                for (size_t k = next.fetch_add(1); k < todo.size(); k = next.fetch_add(1)) compile_unit(h->modules[todo[k]], options, &res[todo[k]]);
+                for (size_t k = next.fetch_add(1); k < todo.size(); k = next.fetch_add(1)) {
+                    if (cancel && *cancel) { res[todo[k]].rc = NVRTC_ERROR_INTERNAL_ERROR; res[todo[k]].log = "error: compile cancelled"; continue; }
+                    compile_unit(jb->modules[todo[k]], options, &res[todo[k]]);
+                }
             });
         for (std::thread& t : pool) t.join();
     }
@@ -383,7 +430,8 @@ int nvrtc_compile(maray_cuda* h) {
             }
             log += rest;
             if (log.size() > 4000) log.resize(4000);
-            return fail(h, MARAY_E_COMPILE, "NVRTC (unit " + std::to_string(i) + "): " + nvrtcGetErrorString(res[i].rc) + "\n" + log);
+            jb->error = "NVRTC (unit " + std::to_string(i) + "): " + nvrtcGetErrorString(res[i].rc) + "\n" + log;
+            return MARAY_E_COMPILE;
         }
         if (std::getenv("MARAY_JIT_VERBOSE")) std::fprintf(stderr, "%s\n", res[i].log.c_str());
         // registers of the kernel from the ptxas -v log: "Function properties for maray_jit" ... "Used N registers"
@@ -394,9 +442,9 @@ int nvrtc_compile(maray_cuda* h) {
             size_t u = log.find("Used ", at);
             if (u != std::string::npos) regs = uint32_t(std::atoi(log.c_str() + u + 5));
         }
-        h->stats.jit_registers = std::max(h->stats.jit_registers, regs);
-        h->cubins[i] = std::move(res[i].cubin);
-        if (!cache_path[i].empty()) cache_store(cache_path[i], h->cubins[i], regs, 1);
+        jb->registers = std::max(jb->registers, regs);
+        jb->cubins[i] = std::move(res[i].cubin);
+        if (!cache_path[i].empty()) cache_store(cache_path[i], jb->cubins[i], regs, 1);
     }
     return MARAY_OK;
 }
@@ -436,6 +484,151 @@ void choose_interp_shape(maray_cuda* h) {
         }
 }
 
+// ---- building and installing the two back ends ------------------------------------------------------
+
+// Code generation + NVRTC for `prog` (tuning knobs from the environment, DESIGN.md "Knobs").  cached_only: succeed
+// only if every unit's cubin is already in the cache directory (nothing is compiled).
+int jit_build(const Program& prog, JitBuild* jb, bool cached_only, const std::atomic<bool>* cancel) {
+    double t1 = now_ms();
+    CodegenOptions copt;
+    if (const char* e = std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = uint32_t(std::strtoul(e, nullptr, 10));
+    if (const char* e = std::getenv("MARAY_JIT_INLINE_TRANS_BELOW")) copt.inline_transcendentals_below = uint32_t(std::strtoul(e, nullptr, 10));
+    if (const char* e = std::getenv("MARAY_JIT_SYNC_EVERY")) copt.sync_every = uint32_t(std::strtoul(e, nullptr, 10));
+    if (const char* e = std::getenv("MARAY_JIT_CONST_BANK")) copt.constants_in_bank = std::strtoul(e, nullptr, 10) != 0;
+    if (const char* e = std::getenv("MARAY_JIT_HOIST")) copt.hoist = std::strtoul(e, nullptr, 10) != 0;
+    if (const char* e = std::getenv("MARAY_JIT_BOOLEAN")) copt.boolean_logic = std::strtoul(e, nullptr, 10) != 0;
+    if (const char* e = std::getenv("MARAY_JIT_SCRATCH")) copt.scratch_batches = std::strtoul(e, nullptr, 10) != 0;
+    if (const char* e = std::getenv("MARAY_JIT_PRIVATE_HELPERS")) copt.private_batch_helpers = std::strtoul(e, nullptr, 10) != 0;
+    if (const char* e = std::getenv("MARAY_JIT_BATCH_WIDTH")) copt.batch_width = uint32_t(std::strtoul(e, nullptr, 10));
+    if (const char* e = std::getenv("MARAY_JIT_BLOCK")) copt.block = uint32_t(std::strtoul(e, nullptr, 10));
+    if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10));
+    jb->maxreg = 0;
+    if (const char* e = std::getenv("MARAY_JIT_MAXREG")) jb->maxreg = unsigned(std::strtoul(e, nullptr, 10));
+    // Programs above the segment size compile as a CHAIN of kernels, one translation unit each (codegen.hpp):
+    // the units compile concurrently on all host cores and nothing is linked.  MARAY_JIT_CHAIN=0 gives round
+    // 1's form (segment functions in one unit) for A/B.  sin/exp/ln stay out of line above the threshold:
+    // inlined, the code of a transcendental-heavy program is several MB of instructions no warp ever re-uses
+    // and the kernel becomes instruction-fetch bound (measured: 33.8 ms inlined vs 18.7 ms out of line on the
+    // 20 000-value deep scene, no_instruction stalls 9.1 per issued instruction; profiles/).
+    if (const char* e = std::getenv("MARAY_JIT_CHAIN")) copt.chain = std::strtoul(e, nullptr, 10) != 0;
+    if (const char* e = std::getenv("MARAY_JIT_CHAIN_SEGMENT_VALUES")) copt.chain_segment_values = uint32_t(std::strtoul(e, nullptr, 10));
+    jb->modules = generate_cuda_modules(prog, copt, &jb->info);
+    if (jb->modules.size() > 1) {
+        CodegenInfo unused;
+        jb->source = generate_cuda_source(prog, copt, &unused);   // the same statements as ONE unit (tooling, tests)
+    } else {
+        jb->source = jb->modules[0];
+    }
+    jb->codegen_ms = now_ms() - t1;
+    if (std::getenv("MARAY_JIT_SOURCE_ONLY")) {   // tooling: inspect the generated text without paying for NVRTC
+        jb->error = "MARAY_JIT_SOURCE_ONLY is set: source generated, not compiled";
+        return MARAY_E_COMPILE;
+    }
+    double t2 = now_ms();
+    int rc = nvrtc_compile(jb, cancel, cached_only);
+    jb->nvrtc_ms = now_ms() - t2;
+    return rc;
+}
+
+void fill_jit_stats(maray_cuda* h) {
+    const JitBuild& jb = h->jit;
+    h->stats.codegen_ms = jb.codegen_ms;
+    h->stats.nvrtc_ms = jb.nvrtc_ms;
+    h->stats.jit_segments = jb.info.segments;
+    h->stats.jit_frame_slots = jb.info.frame_slots;
+    h->stats.jit_source_bytes = uint32_t(jb.source.size());
+    h->stats.jit_units = uint32_t(jb.modules.size());
+    h->stats.jit_compile_threads = jb.compile_threads;
+    h->stats.jit_cache_hit = jb.cache_hit;
+    h->stats.jit_registers = jb.registers;
+    h->stats.jit_cubin_bytes = 0;
+    for (const std::vector<char>& c : jb.cubins) h->stats.jit_cubin_bytes += uint32_t(c.size());
+}
+
+// Makes a finished build the handle's: loads the cubins on every GPU and routes launches to the kernels.
+int jit_install(maray_cuda* h, JitBuild&& jb) {
+    h->jit = std::move(jb);
+    h->jit_block = h->jit.info.block;
+    h->jit_dyn_smem = h->jit.info.dynamic_smem_bytes;
+    h->jit_ncol = h->jit.info.n_col;
+    h->jit_nrow = h->jit.info.n_row;
+    h->jit_chain = h->jit.info.chain;
+    h->jit_frame_slots = h->jit.info.frame_slots;
+    fill_jit_stats(h);
+    double t3 = now_ms();
+    for (Gpu& g : h->gpus) {
+        CU_TRY(h, cudaSetDevice(g.device));
+        h->stats.jit_registers = 0;
+        for (const std::vector<char>& cubin : h->jit.cubins) {
+            cudaLibrary_t lib = nullptr;
+            cudaKernel_t kern = nullptr;
+            CU_TRY(h, cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+            g.libs.push_back(lib);
+            CU_TRY(h, cudaLibraryGetKernel(&kern, lib, kJitKernelName));
+            g.jit_kernels.push_back(kern);
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(kern)) == cudaSuccess)
+                h->stats.jit_registers = std::max(h->stats.jit_registers, uint32_t(fa.numRegs));
+            else cudaGetLastError();
+        }
+        if (h->jit_ncol || h->jit_nrow) {
+            CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_x, g.libs[0], kJitPreXName));
+            CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_y, g.libs[0], kJitPreYName));
+        }
+    }
+    if (!h->gpus.empty()) cudaSetDevice(h->gpus[0].device);
+    h->stats.load_ms += now_ms() - t3;
+    h->use_jit = true;
+    return MARAY_OK;
+}
+
+// Bytecode + launch shape + upload: the interpreter back end is ready when this returns.
+int interp_build_and_install(maray_cuda* h) {
+    double t1 = now_ms();
+    std::string err;
+    // Row-uniform form by default; the all-wide form when the scalar file would crowd out the slot file
+    // (or MARAY_INTERP_UNIFORM=0, for A/B).
+    bool uniform = true;
+    if (const char* e = std::getenv("MARAY_INTERP_UNIFORM")) uniform = std::strtoul(e, nullptr, 10) != 0;
+    if (!compile_bytecode(h->prog, &h->bc, &err, uniform)) return fail(h, MARAY_E_COMPILE, err);
+    if (uniform && h->bc.n_uniform > 4096 && !compile_bytecode(h->prog, &h->bc, &err, false)) return fail(h, MARAY_E_COMPILE, err);
+    choose_interp_shape(h);
+    h->interp_dispatch = 0;
+    if (const char* e = std::getenv("MARAY_INTERP_DISPATCH")) h->interp_dispatch = std::string(e) == "tree" ? 1 : 0;
+    if (!h->interp_block)
+        return fail(h, MARAY_E_UNSUPPORTED, "program needs " + std::to_string(h->bc.n_wide) +
+                                                " live values per pixel, more than the interpreter's shared-memory slot file holds");
+    h->bc_device = bytecode_for_launch(h->bc, h->interp_block * h->interp_ppt / 2, &err);
+    if (h->bc_device.empty()) return fail(h, MARAY_E_UNSUPPORTED, err);
+    if (h->backend == MARAY_BACKEND_INTERP) h->stats.codegen_ms = now_ms() - t1;
+    h->stats.interp_instructions = uint32_t(h->bc.code.size());
+    h->stats.interp_slots = h->bc.n_wide;
+    h->stats.interp_uniform_slots = h->bc.n_uniform;
+    h->stats.interp_block = h->interp_block;
+    h->stats.interp_pixels_per_thread = h->interp_ppt;
+    double t3 = now_ms();
+    for (Gpu& g : h->gpus) {
+        CU_TRY(h, cudaSetDevice(g.device));
+        CU_TRY(h, cudaMalloc(&g.d_code, h->bc_device.size() * sizeof(uint64_t)));
+        CU_TRY(h, cudaMemcpy(g.d_code, h->bc_device.data(), h->bc_device.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CU_TRY(h, cudaMalloc(&g.d_consts, h->bc.consts.size() * sizeof(double)));
+        CU_TRY(h, cudaMemcpy(g.d_consts, h->bc.consts.data(), h->bc.consts.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (!h->gpus.empty()) cudaSetDevice(h->gpus[0].device);
+    h->stats.load_ms += now_ms() - t3;
+    h->have_interp = true;
+    return MARAY_OK;
+}
+
+// MARAY_BACKEND_AUTO: if the background build has finished, make it the handle's.  Called between row chunks.
+int adopt_finished_job(maray_cuda* h) {
+    if (!h->job || h->job->state.load() == 0) return MARAY_OK;
+    if (h->job->th.joinable()) h->job->th.join();
+    std::unique_ptr<JitJob> job = std::move(h->job);
+    if (job->state.load() != 1) return MARAY_OK;          // the build failed: stay on the interpreter (its error is in stats' absence)
+    return jit_install(h, std::move(job->build));
+}
+
 int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint8_t* d_out, double* d_f64,
                 size_t f64_plane, cudaStream_t stream) {
     MrParams p;
@@ -444,7 +637,7 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
     p.out_aligned = (reinterpret_cast<uintptr_t>(d_out) % 16 == 0) ? 1u : 0u;
     p.colv = nullptr; p.rowv = nullptr; p.row_base = 0; p.rows = 0;
     if (n == 0) return MARAY_OK;
-    if (h->backend == MARAY_BACKEND_NVRTC) {
+    if (h->use_jit) {
         if (h->jit_ncol || h->jit_nrow) {
             // Prologue: x-only values once per column, y-only values once per row of this launch.
             const uint32_t y_first = p0 / w, y_last = (p0 + n - 1) / w, rows = y_last - y_first + 1;
@@ -637,6 +830,27 @@ int render_frame_pipelined(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* hos
     return MARAY_OK;
 }
 
+// MARAY_BACKEND_AUTO while NVRTC is still at work: the interpreter renders row chunks of ~30 ms; between
+// chunks the finished build is adopted, and the rest of the frame goes to the generated kernels in one piece.
+int render_frame_tiered(maray_cuda* h, uint32_t w, uint32_t hgt) {
+    uint32_t ya = 0, rows = 8;
+    h->stats.tier_rows_interp = 0;
+    while (ya < hgt) {
+        int rc = adopt_finished_job(h);
+        if (rc) return rc;
+        if (h->use_jit) return render_rows_to_frame(h, w, hgt, ya, hgt);
+        const uint32_t yb = std::min(hgt, ya + rows);
+        double t0 = now_ms();
+        rc = render_rows_to_frame(h, w, hgt, ya, yb);     // synchronises
+        if (rc) return rc;
+        const double ms = std::max(now_ms() - t0, 0.01);
+        h->stats.tier_rows_interp += yb - ya;
+        rows = uint32_t(std::min<double>(std::max<double>(double(yb - ya) * 30.0 / ms, 1.0), 4096.0));
+        ya = yb;
+    }
+    return MARAY_OK;
+}
+
 int render_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
     int rc = check_renderable(h, w, hgt);
     if (rc) return rc;
@@ -646,6 +860,19 @@ int render_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
     if (rc) return rc;
     for (double& k : h->stats.kernel_ms) k = 0.0;
     h->stats.gather_ms = 0.0; h->stats.d2h_ms = 0.0;
+    rc = adopt_finished_job(h);
+    if (rc) return rc;
+    if (h->job && (h->report_kind == MARAY_REPORT_NONE || !h->report_fn)) {
+        rc = render_frame_tiered(h, w, hgt);
+        if (rc) return rc;
+        if (host_rgb) {
+            double t1 = now_ms();
+            CU_TRY(h, cudaMemcpy(host_rgb, g0.d_out, size_t(w) * hgt * 3, cudaMemcpyDeviceToHost));
+            h->stats.d2h_ms = now_ms() - t1;
+        }
+        h->stats.render_ms = now_ms() - t0;
+        return MARAY_OK;
+    }
 
     // Host-bound frames of 4 MiB and more are rendered in row chunks whose device->host copies overlap the
     // chunks still rendering (render_frame_pipelined).  Measured on chess_4k into a pageable buffer: 1 075 ->
@@ -749,7 +976,7 @@ int maray_cuda_create(int n_gpus, const int* device_ids, maray_cuda_t** out) {
 
 void maray_cuda_destroy(maray_cuda_t* h) {
     if (!h) return;
-    release_backend(h);
+    release_backend(h, /*cancel_job=*/false);
     release_textures(h);
     for (Gpu& g : h->gpus) {
         cudaSetDevice(g.device);
@@ -806,11 +1033,12 @@ int maray_cuda_scene_size(const maray_cuda_t* h, uint32_t* w, uint32_t* hgt) {
 int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
     if (!h) return MARAY_E_INVALID;
     if (!h->have_scene) return fail(h, MARAY_E_INVALID, "maray_cuda_compile called before maray_cuda_load_maray");
-    if (backend != MARAY_BACKEND_INTERP && backend != MARAY_BACKEND_NVRTC)
+    if (backend != MARAY_BACKEND_INTERP && backend != MARAY_BACKEND_NVRTC && backend != MARAY_BACKEND_AUTO)
         return fail(h, MARAY_E_INVALID, "unknown back end");
     release_backend(h);
     h->stats = maray_cuda_stats{};
     h->stats.backend = uint32_t(backend);
+    h->backend = backend;
 
     double t0 = now_ms();
     std::vector<TextureDim> dims;
@@ -821,117 +1049,47 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
     h->prog = std::move(prog);
     h->stats.lower_ms = now_ms() - t0;
     fill_program_stats(h);
-
-    double t1 = now_ms();
-    if (backend == MARAY_BACKEND_NVRTC) {
-        CodegenInfo info;
-        CodegenOptions copt;
-        // tuning knobs (documented in DESIGN.md "NVRTC back end")
-        if (const char* e = std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = uint32_t(std::strtoul(e, nullptr, 10));
-        if (const char* e = std::getenv("MARAY_JIT_INLINE_TRANS_BELOW")) copt.inline_transcendentals_below = uint32_t(std::strtoul(e, nullptr, 10));
-        if (const char* e = std::getenv("MARAY_JIT_SYNC_EVERY")) copt.sync_every = uint32_t(std::strtoul(e, nullptr, 10));
-        if (const char* e = std::getenv("MARAY_JIT_CONST_BANK")) copt.constants_in_bank = std::strtoul(e, nullptr, 10) != 0;
-        if (const char* e = std::getenv("MARAY_JIT_HOIST")) copt.hoist = std::strtoul(e, nullptr, 10) != 0;
-        if (const char* e = std::getenv("MARAY_JIT_BOOLEAN")) copt.boolean_logic = std::strtoul(e, nullptr, 10) != 0;
-        if (const char* e = std::getenv("MARAY_JIT_SCRATCH")) copt.scratch_batches = std::strtoul(e, nullptr, 10) != 0;
-        if (const char* e = std::getenv("MARAY_JIT_PRIVATE_HELPERS")) copt.private_batch_helpers = std::strtoul(e, nullptr, 10) != 0;
-        if (const char* e = std::getenv("MARAY_JIT_BATCH_WIDTH")) copt.batch_width = uint32_t(std::strtoul(e, nullptr, 10));
-        if (const char* e = std::getenv("MARAY_JIT_BLOCK")) copt.block = uint32_t(std::strtoul(e, nullptr, 10));
-        if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10));
-        h->jit_maxreg = 0;
-        if (const char* e = std::getenv("MARAY_JIT_MAXREG")) h->jit_maxreg = unsigned(std::strtoul(e, nullptr, 10));
-        // Programs above the segment size compile as a CHAIN of kernels, one translation unit each (codegen.hpp):
-        // the units compile concurrently on all host cores and nothing is linked.  MARAY_JIT_CHAIN=0 gives round
-        // 1's form (segment functions in one unit) for A/B.  sin/exp/ln stay out of line above the threshold:
-        // inlined, the code of a transcendental-heavy program is several MB of instructions no warp ever re-uses
-        // and the kernel becomes instruction-fetch bound (measured: 33.8 ms inlined vs 18.7 ms out of line on the
-        // 20 000-value deep scene, no_instruction stalls 9.1 per issued instruction; profiles/).
-        if (const char* e = std::getenv("MARAY_JIT_CHAIN")) copt.chain = std::strtoul(e, nullptr, 10) != 0;
-        if (copt.chain && !std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = 6144;
-        h->modules = generate_cuda_modules(h->prog, copt, &info);
-        h->jit_chain = info.chain;
-        h->jit_frame_slots = info.frame_slots;
-        if (h->modules.size() > 1) {
-            CodegenInfo unused;
-            h->source = generate_cuda_source(h->prog, copt, &unused);   // the same statements as ONE unit (tooling, tests)
-        } else {
-            h->source = h->modules[0];
-        }
-        h->stats.codegen_ms = now_ms() - t1;
-        h->jit_block = info.block;
-        h->jit_dyn_smem = info.dynamic_smem_bytes;
-        h->jit_ncol = info.n_col;
-        h->jit_nrow = info.n_row;
-        h->stats.jit_segments = info.segments;
-        h->stats.jit_frame_slots = info.frame_slots;
-        h->stats.jit_source_bytes = uint32_t(h->source.size());
-        if (std::getenv("MARAY_JIT_SOURCE_ONLY"))   // tooling: inspect the generated text without paying for NVRTC
-            return fail(h, MARAY_E_COMPILE, "MARAY_JIT_SOURCE_ONLY is set: source generated, not compiled");
-        double t2 = now_ms();
-        int rc = nvrtc_compile(h);
-        h->stats.nvrtc_ms = now_ms() - t2;
-        if (rc) return rc;
-        h->stats.jit_cubin_bytes = 0;
-        for (const std::vector<char>& c : h->cubins) h->stats.jit_cubin_bytes += uint32_t(c.size());
-    } else {
-        // Row-uniform form by default; the all-wide form when the scalar file would crowd out the slot file
-        // (or MARAY_INTERP_UNIFORM=0, for A/B).
-        bool uniform = true;
-        if (const char* e = std::getenv("MARAY_INTERP_UNIFORM")) uniform = std::strtoul(e, nullptr, 10) != 0;
-        if (!compile_bytecode(h->prog, &h->bc, &err, uniform)) return fail(h, MARAY_E_COMPILE, err);
-        if (uniform && h->bc.n_uniform > 4096 && !compile_bytecode(h->prog, &h->bc, &err, false)) return fail(h, MARAY_E_COMPILE, err);
-        choose_interp_shape(h);
-        h->interp_dispatch = 0;
-        if (const char* e = std::getenv("MARAY_INTERP_DISPATCH")) h->interp_dispatch = std::string(e) == "tree" ? 1 : (std::string(e) == "private" ? 2 : 0);
-        if (!h->interp_block)
-            return fail(h, MARAY_E_UNSUPPORTED, "program needs " + std::to_string(h->bc.n_wide) +
-                                                    " live values per pixel, more than the interpreter's shared-memory slot file holds");
-        h->bc_device = bytecode_for_launch(h->bc, h->interp_block * h->interp_ppt / 2, &err);
-        if (h->bc_device.empty()) return fail(h, MARAY_E_UNSUPPORTED, err);
-        h->stats.codegen_ms = now_ms() - t1;
-        h->stats.interp_instructions = uint32_t(h->bc.code.size());
-        h->stats.interp_slots = h->bc.n_wide;
-        h->stats.interp_uniform_slots = h->bc.n_uniform;
-        h->stats.interp_block = h->interp_block;
-        h->stats.interp_pixels_per_thread = h->interp_ppt;
-    }
-    h->backend = backend;
-
-    // Device side: textures, code.
-    double t3 = now_ms();
     if (!h->gpus.empty()) {
         int rc = upload_textures(h);
         if (rc) return rc;
-        for (Gpu& g : h->gpus) {
-            CU_TRY(h, cudaSetDevice(g.device));
-            if (backend == MARAY_BACKEND_NVRTC) {
-                h->stats.jit_registers = 0;
-                for (const std::vector<char>& cubin : h->cubins) {
-                    cudaLibrary_t lib = nullptr;
-                    cudaKernel_t kern = nullptr;
-                    CU_TRY(h, cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-                    g.libs.push_back(lib);
-                    CU_TRY(h, cudaLibraryGetKernel(&kern, lib, kJitKernelName));
-                    g.jit_kernels.push_back(kern);
-                    cudaFuncAttributes fa;
-                    if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(kern)) == cudaSuccess)
-                        h->stats.jit_registers = std::max(h->stats.jit_registers, uint32_t(fa.numRegs));
-                    else cudaGetLastError();
-                }
-                if (h->jit_ncol || h->jit_nrow) {
-                    CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_x, g.libs[0], kJitPreXName));
-                    CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_y, g.libs[0], kJitPreYName));
-                }
-            } else {
-                CU_TRY(h, cudaMalloc(&g.d_code, h->bc_device.size() * sizeof(uint64_t)));
-                CU_TRY(h, cudaMemcpy(g.d_code, h->bc_device.data(), h->bc_device.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
-                CU_TRY(h, cudaMalloc(&g.d_consts, h->bc.consts.size() * sizeof(double)));
-                CU_TRY(h, cudaMemcpy(g.d_consts, h->bc.consts.data(), h->bc.consts.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+
+    int rc = MARAY_OK;
+    if (backend == MARAY_BACKEND_INTERP) {
+        rc = interp_build_and_install(h);
+    } else if (backend == MARAY_BACKEND_NVRTC) {
+        JitBuild jb;
+        rc = jit_build(h->prog, &jb, /*cached_only=*/false, nullptr);
+        if (rc) { h->jit = std::move(jb); fill_jit_stats(h); return fail(h, rc, h->jit.error); }   // the generated text stays inspectable
+        rc = jit_install(h, std::move(jb));
+    } else {
+        // AUTO (time to first frame): cubins already in the cache are used at once.  Otherwise the interpreter --
+        // ready in milliseconds -- renders while NVRTC works on another thread; renders switch to the generated
+        // kernels, between row chunks, as soon as they are built.  Both back ends produce the same bytes.
+        JitBuild jb;
+        rc = jit_build(h->prog, &jb, /*cached_only=*/true, nullptr);
+        if (rc == MARAY_OK) {
+            rc = jit_install(h, std::move(jb));
+        } else {
+            rc = interp_build_and_install(h);
+            if (rc == MARAY_E_UNSUPPORTED) {
+                // the slot file does not fit: compile now, there is nothing to render with meanwhile
+                JitBuild now;
+                rc = jit_build(h->prog, &now, false, nullptr);
+                if (rc) return fail(h, rc, now.error);
+                rc = jit_install(h, std::move(now));
+            } else if (rc == MARAY_OK && !std::getenv("MARAY_JIT_SOURCE_ONLY")) {
+                h->job.reset(new JitJob());
+                JitJob* job = h->job.get();
+                job->prog = h->prog;
+                job->th = std::thread([job] {
+                    job->rc = jit_build(job->prog, &job->build, false, &job->cancel);
+                    job->state = job->rc == MARAY_OK ? 1 : 2;
+                });
             }
         }
-        cudaSetDevice(h->gpus[0].device);
     }
-    h->stats.load_ms = now_ms() - t3;
+    if (rc) return rc;
     h->compiled = true;
     if (stats) *stats = h->stats;
     return MARAY_OK;
@@ -965,6 +1123,8 @@ int maray_cuda_render_band(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t y
     int rc = check_renderable(h, w, hgt);
     if (rc) return rc;
     if (y0 > y1 || y1 > hgt || !d_band) return fail(h, MARAY_E_INVALID, "maray_cuda_render_band: bad band");
+    rc = adopt_finished_job(h);               // MARAY_BACKEND_AUTO: switch to the generated kernels once they are built
+    if (rc) return rc;
     Gpu& g = h->gpus[0];
     CU_TRY(h, cudaSetDevice(g.device));
     return launch_band(h, g, w, y0 * w, (y1 - y0) * w, static_cast<uint8_t*>(d_band), nullptr, 0,
@@ -1004,23 +1164,24 @@ int maray_cuda_render_window_f64(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint
 int maray_cuda_get_stats(const maray_cuda_t* h, maray_cuda_stats* stats) {
     if (!h || !stats) return MARAY_E_INVALID;
     *stats = h->stats;
+    stats->jit_active = h->use_jit ? 1u : 0u;
     return MARAY_OK;
 }
 
 int maray_cuda_get_source(const maray_cuda_t* h, char* buf, size_t cap, size_t* len) {
     if (!h) return MARAY_E_INVALID;
-    if (len) *len = h->source.size();
+    if (len) *len = h->jit.source.size();
     if (buf && cap) {
-        size_t n = std::min(cap - 1, h->source.size());
-        std::memcpy(buf, h->source.data(), n);
+        size_t n = std::min(cap - 1, h->jit.source.size());
+        std::memcpy(buf, h->jit.source.data(), n);
         buf[n] = '\0';
     }
     return MARAY_OK;
 }
 
 int maray_cuda_get_module(const maray_cuda_t* h, uint32_t index, char* buf, size_t cap, size_t* len) {
-    if (!h || index >= h->modules.size()) return MARAY_E_INVALID;
-    const std::string& m = h->modules[index];
+    if (!h || index >= h->jit.modules.size()) return MARAY_E_INVALID;
+    const std::string& m = h->jit.modules[index];
     if (len) *len = m.size();
     if (buf && cap) {
         size_t n = std::min(cap - 1, m.size());

@@ -42,6 +42,9 @@ struct CodegenOptions {
     // concurrently, nothing is linked, no segment pays a call ABI.  false = __noinline__ segment functions in
     // one unit with a per-thread local-memory frame (round 1's form, kept for A/B: MARAY_JIT_CHAIN=0).
     bool chain = true;
+    // Size of a chain segment.  Smaller than segment_values on purpose: the cut-off decides WHETHER a program is
+    // cut (below it one kernel is fastest), this decides how many units compile concurrently once it is.
+    uint32_t chain_segment_values = 6144;
     // Out-of-line sin/exp/ln batches pass arguments and results through per-thread rows of dynamic
     // shared memory to leaf helpers (device_libm.cuh, "scratch-batched form") instead of through the
     // call ABI's registers.  false = the register-argument x4/x2 helpers.

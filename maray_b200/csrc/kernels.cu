@@ -156,8 +156,7 @@ __device__ __forceinline__ void mr_un(const Files<P>& f, double (&acc)[P], doubl
     case BC_H_OUT + (C) * 4 + 2: { double x[P]; mr_fetch<P, 2>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break; \
     case BC_H_OUT + (C) * 4 + 3: { double x[P]; mr_fetch<P, 3>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break;
 
-// DISPATCH: 0 = inline-PTX loop with one shared dispatch site, 1 = C++ switch only (A/B, debugging),
-// 2 = inline-PTX loop whose hottest bodies end in a dispatch of their own.
+// DISPATCH: 0 = inline-PTX inner loop (jump table), 1 = C++ switch only (A/B, debugging).
 template <int P, int DISPATCH>
 __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const uint64_t* __restrict__ code, unsigned int n_instr,
                                                     const double* __restrict__ consts, unsigned int n_consts, unsigned int n_scal,
@@ -226,10 +225,6 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
                 if constexpr (P == 1) MR_INTERP_LOOP_P1(acc[0], sacc, pc, wbase_s, sbase_s, F.half_stride);
                 else if constexpr (P == 2) MR_INTERP_LOOP_P2(acc[0], acc[1], sacc, pc, wbase_s, sbase_s, F.half_stride);
                 else MR_INTERP_LOOP_P4(acc[0], acc[1], acc[2], acc[3], sacc, pc, wbase_s, sbase_s, F.half_stride);
-            } else if constexpr (DISPATCH == 2) {
-                if constexpr (P == 1) MR_INTERP_LOOPX_P1(acc[0], sacc, pc, wbase_s, sbase_s, F.half_stride);
-                else if constexpr (P == 2) MR_INTERP_LOOPX_P2(acc[0], acc[1], sacc, pc, wbase_s, sbase_s, F.half_stride);
-                else MR_INTERP_LOOPX_P4(acc[0], acc[1], acc[2], acc[3], sacc, pc, wbase_s, sbase_s, F.half_stride);
             }
             // One instruction through the C++ switch, which implements EVERY handler (with TREE: all of them).
             const uint64_t w = cs[(pc - cs_s) >> 3];
@@ -362,8 +357,7 @@ cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n
     const unsigned int grid = p.nxb * p.rows;
 #define MR_LAUNCH(PP)                                                                                                         \
     (dispatch == 1 ? launch_interp_as<PP, 1>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream) \
-     : dispatch == 2 ? launch_interp_as<PP, 2>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream) \
-                     : launch_interp_as<PP, 0>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream))
+                   : launch_interp_as<PP, 0>(p, d_code, n_instr, d_consts, n_consts, n_scal, n_wide, all_wide, block, grid, smem, stream))
     switch (pixels_per_thread) {
     case 1: return MR_LAUNCH(1);
     case 2: return MR_LAUNCH(2);

@@ -30,9 +30,8 @@ size_t interp_smem_bytes(unsigned int block, unsigned int pixels_per_thread, uns
 cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n_instr, const double* d_consts,
                           unsigned int n_consts, unsigned int n_uniform, unsigned int n_wide, bool all_wide, unsigned int block,
                           unsigned int pixels_per_thread, cudaStream_t stream, int dispatch = 0);
-// dispatch: 0 = the inline-PTX inner loop with one shared jump-table site (default); 1 = every handler through
-// the C++ switch, which nvcc lowers to a compare-and-branch tree (A/B, debugging: MARAY_INTERP_DISPATCH=tree);
-// 2 = the inline-PTX loop whose hottest bodies end in a dispatch of their own (MARAY_INTERP_DISPATCH=private).
+// dispatch: 0 = the inline-PTX inner loop with its jump table (default); 1 = every handler through the C++
+// switch, which nvcc lowers to a compare-and-branch tree (A/B, debugging: MARAY_INTERP_DISPATCH=tree).
 
 cudaError_t launch_fp64_issue_rate(bool fma, double* d_sink, int iters, int blocks, cudaStream_t stream);
 

@@ -52,7 +52,9 @@ class RenderMethod:
     class Cuda:
         gpus: int = 1
         report: Report = field(default_factory=Report.none)
-        backend: str = "nvrtc"          # "nvrtc" (JIT sibling of wasm.rs) or "interp" (bytecode kernel)
+        # "auto": renders at once (cached cubins, else the bytecode kernel) while NVRTC compiles in the background;
+        # "nvrtc": the JIT sibling of wasm.rs, compiled before the first render; "interp": the bytecode kernel only
+        backend: str = "auto"
         device_ids: Optional[Sequence[int]] = None
 
 
@@ -77,7 +79,7 @@ class Runtime:
         return Runtime(ctx)
 
 
-_BACKENDS = {"interp": _lib.BACKEND_INTERP, "nvrtc": _lib.BACKEND_NVRTC}
+_BACKENDS = {"interp": _lib.BACKEND_INTERP, "nvrtc": _lib.BACKEND_NVRTC, "auto": _lib.BACKEND_AUTO}
 
 
 class CudaRenderer:

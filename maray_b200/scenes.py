@@ -179,8 +179,8 @@ def textured(w: int = 3840, h: int = 2160, n_tex: int = 4) -> bytes:
 def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, window: int = 192) -> bytes:
     """Seeded random DAG of about `n_values` non-constant values, >= 30 % of them sin/exp/ln.
 
-    Leaves u = x/w, v = y/h and 64 "phase fields" L_i = a_i*u + b_i*v + c_j (8 directions x 8 offsets, shared by
-    the whole program).  Every new value combines one or two
+    Leaves u = x/w, v = y/h and 16 "phase fields" L_i = a_i*u + b_i*v + c_j (4 directions x 4 offsets, shared by
+    the whole program -- and live through all of it, which is why there are not more of them).  Every new value combines one or two
     earlier values p, q taken from a sliding window (so the DAG is deep, and the number of simultaneously
     live values stays near `window`):
         sin(k*p + L_i)              k  in {1/8 .. 8/8}
@@ -205,12 +205,12 @@ def deep(w: int = 8192, h: int = 8192, n_values: int = 100_000, seed: int = 5, w
         n = rng.between(lo, hi)
         return E.div(E.nat(n), E.nat(den)) if n >= 0 else E.neg(E.div(E.nat(-n), E.nat(den)))
 
-    dirs = [E.add(E.mul(rat(1, 40, 1), u), E.mul(rat(1, 40, 1), v)) for _ in range(8)]
-    offs = [rat(0, 628, 100) for _ in range(8)]
+    dirs = [E.add(E.mul(rat(1, 40, 1), u), E.mul(rat(1, 40, 1), v)) for _ in range(4)]
+    offs = [rat(0, 628, 100) for _ in range(4)]
     phases = [E.add(d, c) for d in dirs for c in offs]
     pool: List[E.Expr] = []
     uses: List[int] = []
-    count = 8 * 3 + 64
+    count = 4 * 3 + 16
     for _ in range(16):
         f = E.sin(E.add(E.add(E.mul(rat(1, 40, 1), u), E.mul(rat(1, 40, 1), v)), rat(0, 628, 100)))
         pool.append(f); uses.append(0); count += 6

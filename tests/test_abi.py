@@ -104,3 +104,26 @@ def test_texture_dimensions_fold_to_constants():
         assert st["dag_nodes"] == 1 and st["n_const"] == 1 and st["n_tex"] == 0
         code, consts = r.bytecode()
         assert 20.0 in consts.tolist()
+
+
+def test_auto_backend_builds_in_the_background(monkeypatch, tmp_path):
+    """MARAY_BACKEND_AUTO on a host-only handle: with an empty cubin cache the compile call returns with the
+    bytecode ready (milliseconds) while NVRTC works on another thread -- destroy joins it, and the finished cubin
+    lands in the cache --; with the cubin in the cache the generated kernels are installed at once."""
+    import time
+    monkeypatch.setenv("MARAY_JIT_CACHE", str(tmp_path))
+    scene = scenes.sdf(64, 48, 6, seed=4)
+    with CudaRenderer(gpus=0) as r:
+        r.load(scene)
+        t0 = time.perf_counter()
+        st = r.compile("auto")
+        dt = time.perf_counter() - t0
+        assert st["interp_instructions"] > 0 and st["jit_units"] == 0 and r.stats()["jit_active"] == 0
+        assert dt < 5.0
+    # close() joined the background build; its cubin is in the cache now
+    assert any(f.endswith(".mrcubin") for f in os.listdir(tmp_path))
+    with CudaRenderer(gpus=0) as r:
+        r.load(scene)
+        st = r.compile("auto")
+        assert st["jit_cache_hit"] == 1 and st["jit_units"] == 1 and r.stats()["jit_active"] == 1
+        assert "maray_jit" in r.source()

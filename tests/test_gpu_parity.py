@@ -519,6 +519,39 @@ def test_texture_fetch_at_constant_coordinates_on_device(backend):
     assert (np.abs(planes[1] - want[1]) <= 1e-13 * np.abs(want[1])).all()
 
 
+def test_auto_backend_first_frame_and_switch(monkeypatch, tmp_path):
+    """MARAY_BACKEND_AUTO (time to first frame): with an empty cubin cache the first frame comes from the
+    interpreter while NVRTC compiles on another thread; later frames come from the generated kernels.  Same
+    bytes throughout, equal to the plain NVRTC render; a second handle finds the cubin in the cache."""
+    import time
+    scene = scenes.chess_1k()
+    with _renderer(scene, "nvrtc") as r:
+        want = r.render(1024, 1024)
+    monkeypatch.setenv("MARAY_JIT_CACHE", str(tmp_path))
+    with CudaRenderer(gpus=1) as r:
+        r.load(scene)
+        t0 = time.perf_counter()
+        r.compile("auto")
+        first = r.render(1024, 1024)
+        first_s = time.perf_counter() - t0
+        st = r.stats()
+        assert np.array_equal(first, want)
+        assert st["tier_rows_interp"] == 1024 and st["jit_active"] == 0, "the first frame should not have waited for NVRTC"
+        assert first_s < 1.5
+        deadline = time.perf_counter() + 120
+        while not r.stats()["jit_active"] and time.perf_counter() < deadline:
+            time.sleep(0.2)
+            frame = r.render(1024, 1024)
+            assert np.array_equal(frame, want)
+        assert r.stats()["jit_active"] == 1
+        assert np.array_equal(r.render(1024, 1024), want)
+    with CudaRenderer(gpus=1) as r:
+        r.load(scene)
+        st = r.compile("auto")
+        assert st["jit_cache_hit"] == 1 and r.stats()["jit_active"] == 1
+        assert np.array_equal(r.render(1024, 1024), want)
+
+
 def test_multi_gpu_in_process_matches_single():
     import torch
     if torch.cuda.device_count() < 2:

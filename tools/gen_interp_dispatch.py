@@ -236,9 +236,10 @@ def gen(P, PRIVATE_DISPATCH):
 
 def main():
     out = ["// GENERATED by tools/gen_interp_dispatch.py -- do not edit; see that file for the why and the semantics.",
-           "// One macro per pixels-per-thread count: MR_INTERP_LOOP_P<P>(acc..., sacc, pc, wbase, sbase, hs);",
-           "// MR_INTERP_LOOPX_P<P> is the variant whose hottest bodies end in a dispatch of their own."]
-    for P, private in ((1, False), (2, False), (4, False), (1, True), (2, True), (4, True)):
+           "// One macro per pixels-per-thread count: MR_INTERP_LOOP_P<P>(acc..., sacc, pc, wbase, sbase, hs)."]
+    # (A variant whose hottest bodies end in a dispatch of their own -- gen(P, True) -- was measured slower:
+    # chess_1k 104.7 vs 116.6 Mpixel/s; ptxas expands every extra site into its own table of BRA instructions.)
+    for P, private in ((1, False), (2, False), (4, False)):
         lines = gen(P, private)
         accs = ", ".join(f"ACC{k}" for k in range(P))
         out.append(f"#define MR_INTERP_LOOP{'X' if private else ''}_P{P}({accs}, SACC, PC, WBASE, SBASE, HS) \\")
