@@ -144,6 +144,17 @@ int maray_cuda_render_device(maray_cuda_t* h, uint32_t w, uint32_t hgt, void** d
 int maray_cuda_render_band(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t y0, uint32_t y1,
                            void* d_band, void* stream);
 
+/* One process per GPU, frame to be assembled in the first process's GPU memory: that process exports its frame
+ * buffer once (CUDA IPC), the others open it and pass `frame + y0 * w * 3` to maray_cuda_render_band -- their band
+ * kernels then store straight into that memory over NVLink, and no gather step remains.  The exporting handle
+ * keeps the buffer until it renders a larger frame or is destroyed; importers must not outlive it. */
+#define MARAY_IPC_HANDLE_BYTES 64
+int maray_cuda_frame_export(maray_cuda_t* h, uint32_t w, uint32_t hgt, void* handle64, void** d_frame);
+int maray_cuda_frame_import(maray_cuda_t* h, const void* handle64, void** d_frame);
+/* Synchronous device -> host copy on the handle's first GPU (reads back a frame held by maray_cuda_frame_export /
+ * maray_cuda_render_device without the caller needing a CUDA binding of its own). */
+int maray_cuda_copy_to_host(maray_cuda_t* h, const void* d_src, void* host_dst, size_t bytes);
+
 /* Parity instrumentation: the raw f64 channel values of the window [x0,x1) x [y0,y1) of the
  * w x hgt image, as 3 planes of (y1-y0)*(x1-x0) doubles (R, G, B), plus optionally its RGB8. */
 int maray_cuda_render_window_f64(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t x0, uint32_t x1,

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libmaray_cuda.so")
 OK, E_INVALID, E_PARSE, E_SCENE, E_COMPILE, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 BACKEND_INTERP, BACKEND_NVRTC, BACKEND_AUTO = 0, 1, 2
 REPORT_NONE, REPORT_ROW, REPORT_DURATION_MS = 0, 1, 2
+IPC_HANDLE_BYTES = 64
 
 REPORT_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_uint32, ctypes.c_uint32,
                              ctypes.c_double)
@@ -56,6 +57,9 @@ SYMBOLS = [
     ("maray_cuda_render_device", ctypes.c_int, [_P, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(_P),
                                                 ctypes.POINTER(Stats)]),
     ("maray_cuda_render_band", ctypes.c_int, [_P, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _P, _P]),
+    ("maray_cuda_frame_export", ctypes.c_int, [_P, ctypes.c_uint32, ctypes.c_uint32, _P, ctypes.POINTER(_P)]),
+    ("maray_cuda_frame_import", ctypes.c_int, [_P, _P, ctypes.POINTER(_P)]),
+    ("maray_cuda_copy_to_host", ctypes.c_int, [_P, _P, _P, ctypes.c_size_t]),
     ("maray_cuda_render_window_f64", ctypes.c_int, [_P] + [ctypes.c_uint32] * 6 + [_P, _P]),
     ("maray_cuda_get_stats", ctypes.c_int, [_P, ctypes.POINTER(Stats)]),
     ("maray_cuda_get_source", ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),

@@ -108,6 +108,7 @@ struct maray_cuda {
     int backend = -1;                   // as asked for: MARAY_BACKEND_*
     bool use_jit = false;               // launches go to the generated kernels (else: to the interpreter)
     bool have_interp = false;           // bytecode compiled (and uploaded when there are GPUs)
+    std::vector<void*> imported;        // frames of other processes opened with maray_cuda_frame_import
     std::unique_ptr<JitJob> job;        // MARAY_BACKEND_AUTO: the NVRTC build in flight, or finished and not yet installed
     JitBuild jit;                       // the installed build
     Bytecode bc;
@@ -851,6 +852,50 @@ int render_frame_tiered(maray_cuda* h, uint32_t w, uint32_t hgt) {
     return MARAY_OK;
 }
 
+// Several GPUs, frame wanted in host memory: every GPU renders its row band into its own buffer and copies it
+// straight into the caller's image over its own PCIe link, one host thread per GPU (a pageable destination
+// makes the copy call synchronous, so the threads are what lets the copies overlap).  No gather: bands only
+// have to meet in GPU 0's memory when the frame is to stay on the device (render_rows_to_frame).
+int render_frame_bands_to_host(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
+    const size_t G = h->gpus.size();
+    std::vector<int> rcs(G, MARAY_OK);
+    std::vector<float> kms(G, 0.f);
+    std::vector<double> copy_ms(G, 0.0);
+    std::vector<std::thread> pool;
+    for (size_t gi = 0; gi < G; gi++)
+        pool.emplace_back([&, gi] {
+            Gpu& g = h->gpus[gi];
+            const uint32_t y0 = uint32_t(uint64_t(hgt) * gi / G), y1 = uint32_t(uint64_t(hgt) * (gi + 1) / G);
+            const size_t bytes = size_t(y1 - y0) * w * 3;
+            if (!bytes) return;
+            auto body = [&]() -> int {
+                CU_TRY(h, cudaSetDevice(g.device));
+                int rc = ensure_out(h, g, gi == 0 ? size_t(w) * hgt * 3 : bytes);
+                if (rc) return rc;
+                uint8_t* dst = gi == 0 ? g.d_out + size_t(y0) * w * 3 : g.d_out;
+                CU_TRY(h, cudaEventRecord(g.ev0, g.stream));
+                rc = launch_band(h, g, w, y0 * w, (y1 - y0) * w, dst, nullptr, 0, g.stream);
+                if (rc) return rc;
+                CU_TRY(h, cudaEventRecord(g.ev1, g.stream));
+                CU_TRY(h, cudaStreamSynchronize(g.stream));
+                double t1 = now_ms();
+                CU_TRY(h, cudaMemcpy(host_rgb + size_t(y0) * w * 3, dst, bytes, cudaMemcpyDeviceToHost));
+                copy_ms[gi] = now_ms() - t1;
+                CU_TRY(h, cudaEventElapsedTime(&kms[gi], g.ev0, g.ev1));
+                return MARAY_OK;
+            };
+            rcs[gi] = body();
+        });
+    for (std::thread& t : pool) t.join();
+    cudaSetDevice(h->gpus[0].device);
+    for (size_t gi = 0; gi < G; gi++) {
+        if (rcs[gi]) return rcs[gi];
+        if (gi < 8) h->stats.kernel_ms[gi] = kms[gi];
+        h->stats.d2h_ms = std::max(h->stats.d2h_ms, copy_ms[gi]);
+    }
+    return MARAY_OK;
+}
+
 int render_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
     int rc = check_renderable(h, w, hgt);
     if (rc) return rc;
@@ -882,6 +927,9 @@ int render_frame(maray_cuda* h, uint32_t w, uint32_t hgt, uint8_t* host_rgb) {
     if (host_rgb && h->gpus.size() == 1 && pipelined &&
         (h->report_kind == MARAY_REPORT_NONE || !h->report_fn) && size_t(w) * hgt * 3 >= (size_t(4) << 20)) {
         rc = render_frame_pipelined(h, w, hgt, host_rgb);
+        if (rc) return rc;
+    } else if (host_rgb && h->gpus.size() > 1 && hgt >= h->gpus.size() && (h->report_kind == MARAY_REPORT_NONE || !h->report_fn)) {
+        rc = render_frame_bands_to_host(h, w, hgt, host_rgb);
         if (rc) return rc;
     } else if (h->report_kind == MARAY_REPORT_NONE || !h->report_fn || !host_rgb) {
         rc = render_rows_to_frame(h, w, hgt, 0, hgt);
@@ -978,6 +1026,10 @@ void maray_cuda_destroy(maray_cuda_t* h) {
     if (!h) return;
     release_backend(h, /*cancel_job=*/false);
     release_textures(h);
+    if (!h->gpus.empty() && !h->imported.empty()) {
+        cudaSetDevice(h->gpus[0].device);
+        for (void* p : h->imported) cudaIpcCloseMemHandle(p);
+    }
     for (Gpu& g : h->gpus) {
         cudaSetDevice(g.device);
         if (g.d_out) cudaFree(g.d_out);
@@ -1129,6 +1181,43 @@ int maray_cuda_render_band(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t y
     CU_TRY(h, cudaSetDevice(g.device));
     return launch_band(h, g, w, y0 * w, (y1 - y0) * w, static_cast<uint8_t*>(d_band), nullptr, 0,
                        static_cast<cudaStream_t>(stream));
+}
+
+int maray_cuda_frame_export(maray_cuda_t* h, uint32_t w, uint32_t hgt, void* handle64, void** d_frame) {
+    int rc = check_renderable(h, w, hgt);
+    if (rc) return rc;
+    if (!handle64 || !d_frame) return fail(h, MARAY_E_INVALID, "maray_cuda_frame_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MARAY_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    Gpu& g = h->gpus[0];
+    CU_TRY(h, cudaSetDevice(g.device));
+    rc = ensure_out(h, g, size_t(w) * hgt * 3);
+    if (rc) return rc;
+    cudaIpcMemHandle_t hd;
+    CU_TRY(h, cudaIpcGetMemHandle(&hd, g.d_out));
+    std::memcpy(handle64, &hd, sizeof hd);
+    *d_frame = g.d_out;
+    return MARAY_OK;
+}
+
+int maray_cuda_frame_import(maray_cuda_t* h, const void* handle64, void** d_frame) {
+    if (!h || !handle64 || !d_frame) return fail(h, MARAY_E_INVALID, "maray_cuda_frame_import: null argument");
+    if (h->gpus.empty()) return fail(h, MARAY_E_CUDA, "host-only handle");
+    CU_TRY(h, cudaSetDevice(h->gpus[0].device));
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle64, sizeof hd);
+    void* p = nullptr;
+    CU_TRY(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->imported.push_back(p);
+    *d_frame = p;
+    return MARAY_OK;
+}
+
+int maray_cuda_copy_to_host(maray_cuda_t* h, const void* d_src, void* host_dst, size_t bytes) {
+    if (!h || !d_src || !host_dst) return fail(h, MARAY_E_INVALID, "maray_cuda_copy_to_host: null argument");
+    if (h->gpus.empty()) return fail(h, MARAY_E_CUDA, "host-only handle");
+    CU_TRY(h, cudaSetDevice(h->gpus[0].device));
+    CU_TRY(h, cudaMemcpy(host_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return MARAY_OK;
 }
 
 int maray_cuda_render_window_f64(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t x0, uint32_t x1, uint32_t y0,

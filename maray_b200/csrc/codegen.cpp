@@ -260,9 +260,10 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
     uint64_t n_trans = prog.stats.op_count[OP_SIN] + prog.stats.op_count[OP_EXP] + prog.stats.op_count[OP_LN];
 
     const uint32_t cut_off = opt.segment_values ? opt.segment_values : 4096;
-    const bool segmented = order.size() > cut_off;
-    const bool chain = segmented && opt.chain && !hoist;
+    bool segmented = order.size() > cut_off;
+    bool chain = segmented && opt.chain && !hoist;
     const uint32_t seg_len = chain ? std::max(256u, std::min(cut_off, opt.chain_segment_values)) : cut_off;
+    if (chain && order.size() <= seg_len) segmented = chain = false;      // a chain of one kernel is a plain kernel
     // chain: cut into equal parts (the last kernel is not a stub)
     const uint32_t n_seg = segmented ? uint32_t((order.size() + seg_len - 1) / seg_len) : 1;
     const uint32_t seg_size = segmented ? uint32_t((order.size() + n_seg - 1) / n_seg) : uint32_t(order.size());

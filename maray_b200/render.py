@@ -217,6 +217,22 @@ class CudaRenderer:
     def render_band(self, w: int, h: int, y0: int, y1: int, d_band: int, stream: int = 0) -> None:
         self._check(self._L.maray_cuda_render_band(self._h, w, h, y0, y1, ctypes.c_void_p(d_band), ctypes.c_void_p(stream)))
 
+    def frame_export(self, w: int, h: int):
+        """(handle bytes, device pointer) of this handle's frame buffer on its first GPU, for other processes to
+        open with frame_import and render their bands into (maray_cuda_frame_export)."""
+        buf = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        p = ctypes.c_void_p()
+        self._check(self._L.maray_cuda_frame_export(self._h, w, h, buf, ctypes.byref(p)))
+        return buf.raw, p.value
+
+    def frame_import(self, handle: bytes) -> int:
+        p = ctypes.c_void_p()
+        self._check(self._L.maray_cuda_frame_import(self._h, ctypes.c_char_p(handle), ctypes.byref(p)))
+        return p.value
+
+    def copy_to_host(self, d_src: int, out: np.ndarray) -> None:
+        self._check(self._L.maray_cuda_copy_to_host(self._h, ctypes.c_void_p(d_src), out.ctypes.data, out.nbytes))
+
     def render_window_f64(self, w: int, h: int, x0: int, x1: int, y0: int, y1: int):
         """(planes float64 (3, y1-y0, x1-x0), rgb uint8 (y1-y0, x1-x0, 3)) of that window."""
         planes = np.zeros((3, y1 - y0, x1 - x0), dtype=np.float64)

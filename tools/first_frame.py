@@ -42,7 +42,8 @@ for backend in backends:
     t3 = time.perf_counter()
     after = r.stats()
     rec = {"workload": spec, "backend": backend, "first_frame_s": round(t3 - t0, 4), "load_s": round(t1 - t0, 4),
-           "compile_call_s": round(t2 - t1, 4), "render_call_s": round(t3 - t2, 4), "lower_ms": round(st["lower_ms"], 1),
+           "compile_call_s": round(t2 - t1, 4), "render_call_s": round(t3 - t2, 4), "lower_ms": round(st["lower_ms"], 1), "codegen_ms": round(st["codegen_ms"], 1), "nvrtc_ms": round(st["nvrtc_ms"], 1),
+           "cache_hit": st["jit_cache_hit"], "compile_threads": st["jit_compile_threads"], "cache_dir": os.environ["MARAY_JIT_CACHE"],
            "rows_by_interpreter": after["tier_rows_interp"], "jit_active_after": after["jit_active"],
            "rgb_sha": hashlib.sha256(img.tobytes()).hexdigest()[:16]}
     t4 = time.perf_counter()
