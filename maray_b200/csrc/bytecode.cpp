@@ -73,6 +73,7 @@ public:
             next_of_shape[s] = uint32_t(i);
         }
 
+        seq_ = &seq;
         for (size_t i = 0; i < seq.size() && err.empty(); i++) gen(seq[i], uint32_t(i), next_same[i]);
 
         // channels whose value is a constant, X or Y (everything else was written when computed)
@@ -97,6 +98,21 @@ private:
     std::vector<int32_t> wslot, uslot, kidx;
     std::vector<uint32_t> free_wide;
     uint32_t acc_holds = NONE, sacc_holds = NONE;
+    bool acc_negated = false;        // acc_holds is a `neg` whose negation has been left to its only consumer
+    const std::vector<uint32_t>* seq_ = nullptr;
+
+    // `neg` of the accumulator, read once, by the next wide instruction, which is a binary operation with the
+    // negated value as exactly one operand: the negation rides on that instruction (BC_H_BINN) and this one
+    // is not emitted.  Same arithmetic, one dispatch less (14 % of the shipped chess scene's instructions).
+    bool neg_can_ride(uint32_t id, uint32_t next_same_shape) const {
+        const Node& n = P.nodes[id];
+        if (n.op != OP_NEG || scalar_shape(id) || acc_holds != n.a || acc_negated) return false;
+        if (next_same_shape == NONE || uses_left[id] != 1 || last_use[id] != next_same_shape) return false;
+        for (int c = 0; c < 3; c++) if (P.root[c] == id) return false;
+        const Node& u = P.nodes[(*seq_)[next_same_shape]];
+        if (u.op != OP_ADD && u.op != OP_MUL && u.op != OP_MAX && u.op != OP_MIN) return false;
+        return (u.a == id) != (u.b == id);
+    }
 
     bool is_const(uint32_t id) const { return P.nodes[id].op == OP_CONST; }
     // Values that do not depend on x are one number per block (every block lies inside one row).
@@ -140,6 +156,13 @@ private:
         const bool sc = scalar_shape(id);
         uint32_t ka = 0, kb = 0, a = 0, b = 0, dst = 0;
         BcOp op = BC_END;
+        if (neg_can_ride(id, next_same_shape)) {
+            consume(n.a);
+            acc_holds = id;
+            acc_negated = true;
+            return;
+        }
+        const bool neg_acc = acc_negated;      // this instruction is the consumer the negation was left to
         if (op_is_unary(n.op)) {
             op = BcOp(BC_NEG + (n.op - OP_NEG));
             if (!operand(n.a, &ka, &a)) return;
@@ -161,7 +184,12 @@ private:
             err = "internal: scalar instruction with a wide operand";
             return;
         }
-        emit(bc_handler(op, sc, ka, kb), (ka << BC_F_KA_SHIFT) | (kb << BC_F_KB_SHIFT), dst, a, b);
+        if (neg_acc && (sc || !(op >= BC_ADD && op <= BC_MIN) || (ka == BC_K_A) == (kb == BC_K_A))) {
+            err = "internal: a deferred negation met an instruction that cannot carry it";
+            return;
+        }
+        acc_negated = false;
+        emit(bc_handler(op, sc, ka, kb, neg_acc), (ka << BC_F_KA_SHIFT) | (kb << BC_F_KB_SHIFT) | (neg_acc ? BC_F_NEG_ACC : 0u), dst, a, b);
         consume(n.a);
         if (op_is_binary(n.op)) consume(n.b);
         if (!err.empty()) return;
@@ -210,10 +238,10 @@ std::vector<uint64_t> bytecode_for_launch(const Bytecode& bc, uint32_t slot16, s
     for (uint64_t w : bc.code) {
         const uint32_t h = uint32_t(w) & 0xff, fl = uint32_t(w >> 8) & 0xff;
         if (h == BC_H_END) break;                      // the padding below ends the stream
-        if (h < BC_H_SCALAR) {
+        if (h < BC_H_SCALAR || h >= BC_H_BINN) {
             uint64_t dst = (w >> 16) & 0xffff, a = (w >> 32) & 0xffff, b = (w >> 48) & 0xffff;
             if (((fl >> BC_F_KA_SHIFT) & 3u) == BC_K_W) a *= slot16;
-            const bool binary = (h >= BC_H_BIN && h < BC_H_UN) || h == BC_H_TEX;
+            const bool binary = (h >= BC_H_BIN && h < BC_H_UN) || h == BC_H_TEX || h >= BC_H_BINN;
             if (binary && ((fl >> BC_F_KB_SHIFT) & 3u) == BC_K_W) b *= slot16;
             if ((fl & BC_F_STORE) && h != BC_H_TEX) dst *= slot16;
             w = (w & 0xffffull) | (dst << 16) | (a << 32) | (b << 48);

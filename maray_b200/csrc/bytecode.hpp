@@ -71,9 +71,14 @@ constexpr uint32_t BC_H_SCALAR = 144;                  // first scalar-shape id
 constexpr uint32_t BC_H_SBIN = 144;                    // 144 .. 159
 constexpr uint32_t BC_H_SUN = 160;                     // 160 .. 177
 constexpr uint32_t BC_H_STEX = 178;
-constexpr uint32_t BC_H_COUNT = 179;
+// Wide binary operation whose accumulator operand is NEGATED first (fuses `neg` into its only consumer; the
+// arithmetic is unchanged: x + (-acc), (-acc) * y, max/min of the negated value -- what the scene computes):
+//   BC_H_BINN + (op - BC_ADD) * 6 + c,  c = 0..2: (A, W|S|T), 3..5: (W|S|T, A);  flags carry BC_F_NEG_ACC.
+constexpr uint32_t BC_H_BINN = 179;                    // 179 .. 202
+constexpr uint32_t BC_H_COUNT = 203;
 
 constexpr uint32_t BC_F_STORE = 1u;                    // store the result to slot dst of the shape's file
+constexpr uint32_t BC_F_NEG_ACC = 2u;                  // the accumulator operand is negated (BC_H_BINN handlers)
 constexpr uint32_t BC_F_KA_SHIFT = 2, BC_F_KB_SHIFT = 4;   // operand kinds (BcKind), two bits each
 
 struct Bytecode {
@@ -88,8 +93,9 @@ inline uint64_t bc_encode(uint32_t handler, uint32_t flags, uint32_t dst, uint32
     return uint64_t(handler & 0xff) | (uint64_t(flags & 0xff) << 8) | (uint64_t(dst & 0xffff) << 16) |
            (uint64_t(a & 0xffff) << 32) | (uint64_t(b & 0xffff) << 48);
 }
-inline uint32_t bc_handler(BcOp op, bool scalar_shape, uint32_t ka, uint32_t kb) {
+inline uint32_t bc_handler(BcOp op, bool scalar_shape, uint32_t ka, uint32_t kb, bool neg_acc = false) {
     if (op == BC_END) return BC_H_END;
+    if (neg_acc) return BC_H_BINN + (op - BC_ADD) * 6 + (ka == BC_K_A ? kb - 1 : 3 + (ka - 1));
     if (scalar_shape) {
         const uint32_t ta = ka == BC_K_T ? 1u : 0u, tb = kb == BC_K_T ? 1u : 0u;
         if (op >= BC_ADD && op <= BC_MIN) return BC_H_SBIN + (op - BC_ADD) * 4 + ta * 2 + tb;

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
             const unsigned int h = lo & 0xffu;
             const unsigned int a = hi & 0xffffu, b = hi >> 16;   // wide indices pre-scaled by the host: see Files
             if (h <= BC_H_YIELD) break;                          // YIELD: next chunk; END: the last chunk is done
-            if (h < BC_H_SCALAR) {
+            if (h < BC_H_SCALAR || h >= BC_H_BINN) {
                 switch (h) {
                     MR_BIN_CASES(0, OpAdd)
                     MR_BIN_CASES(1, OpMul)
@@ -260,7 +260,25 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
 #pragma unroll
                     for (int k = 0; k < P; k++) acc[k] = mr_tex(t.data, t.w, t.h, imm & 3u, x[k], y[k]);
                 } break;
-                default: break;
+                default:
+                    if (h >= BC_H_BINN) {
+                        // binary operation whose accumulator operand is negated first (a `neg` fused into its consumer)
+                        const unsigned int ka = (lo >> (8 + BC_F_KA_SHIFT)) & 3u, kb = (lo >> (8 + BC_F_KB_SHIFT)) & 3u;
+                        double x[P], y[P];
+                        mr_fetch_rt<P>(F, acc, sacc, ka, a, x);
+                        mr_fetch_rt<P>(F, acc, sacc, kb, b, y);
+#pragma unroll
+                        for (int k = 0; k < P; k++) {
+                            if (ka == BC_K_A) x[k] = -x[k]; else y[k] = -y[k];
+                            switch ((h - BC_H_BINN) / 6u) {
+                            case 0: acc[k] = x[k] + y[k]; break;
+                            case 1: acc[k] = x[k] * y[k]; break;
+                            case 2: acc[k] = mr_max(x[k], y[k]); break;
+                            default: acc[k] = mr_min(x[k], y[k]); break;
+                            }
+                        }
+                    }
+                    break;
                 }
                 if ((lo & (BC_F_STORE << 8)) && h != BC_H_TEX) F.store(lo >> 16, acc);
             } else {

@@ -201,22 +201,28 @@ def host_chain_run(modules, w: int, p0: int, n: int, frame_slots: int, textures=
 (BC_END, BC_MOV, BC_ADD, BC_MUL, BC_MAX, BC_MIN, BC_NEG, BC_ABS, BC_RECIP, BC_SQRT, BC_STEP, BC_SIN, BC_EXP, BC_LN,
  BC_TEX, BC_OUT_R, BC_OUT_G, BC_OUT_B) = range(18)
 K_A, K_W, K_S, K_T = 0, 1, 2, 3
-H_END, H_BIN, H_UN, H_OUT, H_TEX, H_SCALAR, H_SBIN, H_SUN, H_STEX, H_COUNT = 0, 16, 80, 116, 128, 144, 144, 160, 178, 179
-F_STORE, F_KA_SHIFT, F_KB_SHIFT = 1, 2, 4
+H_END, H_BIN, H_UN, H_OUT, H_TEX, H_SCALAR, H_SBIN, H_SUN, H_STEX, H_BINN, H_COUNT = 0, 16, 80, 116, 128, 144, 144, 160, 178, 179, 203
+F_STORE, F_NEG_ACC, F_KA_SHIFT, F_KB_SHIFT = 1, 2, 2, 4
 
 
 def bc_decode(w):
     """(shape_is_scalar, op, ka, kb, store, dst, a, b) of one instruction word; checks that the handler id
     and the flags agree on the operand kinds (the kernel's specialised bodies read the id, its generic
-    bodies the flags)."""
+    bodies the flags).  op + 100: the accumulator operand is negated first (BC_H_BINN)."""
     w = int(w)
     h, fl, dst, a, b = w & 0xFF, (w >> 8) & 0xFF, (w >> 16) & 0xFFFF, (w >> 32) & 0xFFFF, (w >> 48) & 0xFFFF
     ka, kb = (fl >> F_KA_SHIFT) & 3, (fl >> F_KB_SHIFT) & 3
     store = bool(fl & F_STORE)
     if h == H_END:
         return False, BC_END, 0, 0, False, 0, 0, 0
+    if h >= H_BINN:
+        assert h < H_COUNT and (fl & F_NEG_ACC) and (ka == K_A) != (kb == K_A)
+        c = (h - H_BINN) % 6
+        assert c == (kb - 1 if ka == K_A else 3 + ka - 1), "handler id and flags disagree on the operand kinds"
+        return False, 100 + BC_ADD + (h - H_BINN) // 6, ka, kb, store, dst, a, b
+    assert not (fl & F_NEG_ACC)
     if h >= H_SCALAR:
-        assert h < H_COUNT and ka in (K_S, K_T), "scalar instruction with a wide operand"
+        assert h < H_BINN and ka in (K_S, K_T), "scalar instruction with a wide operand"
         if h < H_SUN:
             op = BC_ADD + (h - H_SBIN) // 4
             assert kb in (K_S, K_T) and (h - H_SBIN) % 4 == (ka == K_T) * 2 + (kb == K_T), "handler id and flags disagree"
@@ -348,6 +354,14 @@ def bytecode_run(code, consts, xs, ys, textures=(), row_uniform=True):
                     assert op != BC_TEX, "TEX keeps its texture id in the dst field and must not store"
                     assert dst >= nk and dst not in scal, "row-uniform slots are never recycled"
                     scal[dst] = sacc
+                continue
+            if op >= 100:                         # the accumulator operand is negated first
+                op -= 100
+                x = -acc if ka == K_A else wide_operand(ka, a)
+                y = -acc if kb == K_A else wide_operand(kb, b)
+                acc = apply(op, x, y, dst)
+                if store:
+                    wide[dst] = acc
                 continue
             x = wide_operand(ka, a)
             if BC_OUT_R <= op <= BC_OUT_B:

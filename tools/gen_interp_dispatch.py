@@ -28,7 +28,7 @@ import sys
 
 # handler ids: keep in step with csrc/bytecode.hpp
 H_BIN, H_UN, H_OUT, H_TEX = 16, 80, 116, 128
-H_SBIN, H_SUN, H_STEX, H_COUNT = 144, 160, 178, 179
+H_SBIN, H_SUN, H_STEX, H_BINN, H_COUNT = 144, 160, 178, 179, 203
 A, W, S, T = 0, 1, 2, 3
 BIN_OPS = ["add", "mul", "max", "min"]
 UN_OPS = {0: "neg", 1: "abs", 4: "step", 8: "mov"}          # u index -> op (others: C++ switch)
@@ -193,6 +193,20 @@ def gen(P, PRIVATE_DISPATCH):
                     body(f"H{hid}{sfx}", [("a", ka, xs), ("b", kb, ys)], store, "wide", compute,
                          hot=(op in ("add", "mul") and (ka, kb) in ((A, S), (A, W), (S, A), (W, A), (W, S), (W, W), (S, W)))
                              or (op in ("max", "min") and (ka, kb) in ((A, W), (W, A), (A, S), (S, A))))
+        # wide binary with the accumulator operand negated first (a `neg` fused into its only consumer)
+        for oi, op in enumerate(BIN_OPS):
+            for c, (ka, kb) in enumerate(((A, W), (A, S), (A, T), (W, A), (S, A), (T, A))):
+                hid = H_BINN + oi * 6 + c
+                targets[hid + 256 * store] = f"H{hid}{sfx}"
+
+                def compute(srcs, op=op, ka=ka):
+                    x, y = srcs
+                    neg = ys if ka == A else xs            # the temporaries of the operand that is the accumulator are free
+                    for k in range(P):
+                        emit(f"neg.f64 {neg[k]}, {acc[k]};")
+                    for k in range(P):
+                        binop(op, acc[k], neg[k] if ka == A else x[k], y[k] if ka == A else neg[k])
+                body(f"H{hid}{sfx}", [("a", ka, xs), ("b", kb, ys)], store, "wide", compute)
         # wide unary
         for u, op in UN_OPS.items():
             for ka in range(4):
