@@ -337,6 +337,18 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_barrier(tag):
+        """Barrier through the rendezvous store: the waiting ranks hold no GPU (an NCCL barrier parks a spinning
+        kernel on every waiting rank's GPU, which would time-slice against rank 0's in-process render there)."""
+        if world == 1:
+            return
+        torch.cuda.synchronize()
+        store = dist.distributed_c10d._get_default_store()
+        key = f"maray_bench_{name}_{tag}"
+        store.add(key, 1)
+        while int(store.add(key, 0)) < world:
+            time.sleep(0.002)
+
     # compile: rank 0 first, so that the other ranks find its cubins in the cache instead of all running NVRTC at once
     r = CudaRenderer(device_ids=[local_rank])
     r.set_textures(textures)
@@ -443,6 +455,11 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         dist.broadcast_object_list(name_box, src=0)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=name_box[0])
+            try:        # attaching registers the segment with this process's resource tracker, which would unlink it at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         host_frame = np.ndarray((h * w * 3,), dtype=np.uint8, buffer=shm.buf)
         rt = torch.cuda.cudart()
         reg_rc = rt.cudaHostRegister(host_frame.ctypes.data, h * w * 3, 0)
@@ -479,6 +496,7 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
     # ---- the same split through ONE process: maray_cuda_create(N) from rank 0 (what a Rust host calls) ----
     e2e_inprocess = None
     if world > 1:
+        host_barrier("inprocess_begin")
         if rank == 0:
             try:
                 with CudaRenderer(device_ids=list(range(world))) as rr:
@@ -497,6 +515,7 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
                                             "process: one host thread per GPU renders its band and copies it out"}
             except Exception as exc:
                 e2e_inprocess = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        host_barrier("inprocess_end")
         barrier()
 
     rec = None

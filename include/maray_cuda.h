@@ -130,11 +130,13 @@ int maray_cuda_set_report(maray_cuda_t* h, int kind, uint32_t every, maray_repor
 
 /* `gen_to_image(method, rt, color, &mut img, report)` (reference src/lib.rs:1177-1195):
  * renders a w x h image into the caller's HOST buffer `rgb` (w*h*3 bytes, the raw RgbImage layout,
- * so Rust passes img.as_mut_ptr()).  Rows are split into contiguous bands over the handle's GPUs,
- * bands are gathered on GPU 0 by peer copy and copied to `rgb`. */
+ * so Rust passes img.as_mut_ptr(); a pageable Vec<u8> is the expected case).  One GPU: the frame is rendered
+ * in row chunks whose device->host copies overlap the chunks still rendering.  Several GPUs: rows are split
+ * into contiguous bands, every GPU renders its band and copies it into `rgb` over its own PCIe link. */
 int maray_cuda_render(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint8_t* rgb, maray_cuda_stats* stats);
 
-/* Same, but the finished frame stays in device memory on the handle's first GPU:
+/* Same, but the finished frame stays in device memory on the handle's first GPU (bands of the other GPUs
+ * are gathered there by peer copy over NVLink -- the only exchange step of the path):
  * *d_rgb receives a device pointer (owned by the handle, valid until the next render/destroy). */
 int maray_cuda_render_device(maray_cuda_t* h, uint32_t w, uint32_t hgt, void** d_rgb, maray_cuda_stats* stats);
 

@@ -201,7 +201,7 @@ def gen(P, PRIVATE_DISPATCH):
 
                 def compute(srcs, op=op, ka=ka):
                     x, y = srcs
-                    neg = ys if ka == A else xs            # the temporaries of the operand that is the accumulator are free
+                    neg = xs if ka == A else ys            # the temporaries of the operand that is the accumulator are free
                     for k in range(P):
                         emit(f"neg.f64 {neg[k]}, {acc[k]};")
                     for k in range(P):
