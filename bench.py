@@ -338,16 +338,8 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         torch.cuda.synchronize()
 
     def host_barrier(tag):
-        """Barrier through the rendezvous store: the waiting ranks hold no GPU (an NCCL barrier parks a spinning
-        kernel on every waiting rank's GPU, which would time-slice against rank 0's in-process render there)."""
-        if world == 1:
-            return
         torch.cuda.synchronize()
-        store = dist.distributed_c10d._get_default_store()
-        key = f"maray_bench_{name}_{tag}"
-        store.add(key, 1)
-        while int(store.add(key, 0)) < world:
-            time.sleep(0.002)
+        bands.host_barrier(f"{name}_{tag}", world)
 
     # compile: rank 0 first, so that the other ranks find its cubins in the cache instead of all running NVRTC at once
     r = CudaRenderer(device_ids=[local_rank])
@@ -447,25 +439,11 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         e2e_pinned = e2e_with(torch.zeros((h, w, 3), dtype=torch.uint8).pin_memory().numpy())
         e2e_how = "maray_cuda_render into a pageable host image (pipelined row chunks)"
     else:
-        from multiprocessing import shared_memory
-        name_box = [None]
-        if rank == 0:
-            shm = shared_memory.SharedMemory(create=True, size=h * w * 3)
-            name_box[0] = shm.name
-        dist.broadcast_object_list(name_box, src=0)
-        if rank != 0:
-            shm = shared_memory.SharedMemory(name=name_box[0])
-            try:        # attaching registers the segment with this process's resource tracker, which would unlink it at exit
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(shm._name, "shared_memory")
-            except Exception:
-                pass
-        host_frame = np.ndarray((h * w * 3,), dtype=np.uint8, buffer=shm.buf)
-        rt = torch.cuda.cudart()
-        reg_rc = rt.cudaHostRegister(host_frame.ctypes.data, h * w * 3, 0)
+        shm = bands.SharedHostFrame(w, h, rank, world)
+        reg_rc = shm.pin()
         band_dev = torch.empty(max(1, (y1 - y0) * w * 3), dtype=torch.uint8, device=dev)
         nbytes = (y1 - y0) * w * 3
-        host_band = torch.from_numpy(host_frame)[y0 * w * 3: y1 * w * 3]      # this rank's rows of the shared host frame
+        host_band = shm.band_view(y0, y1)                                      # this rank's rows of the shared host frame
         pinned = bool(host_band.is_pinned()) if nbytes else True
 
         def step_e2e():
@@ -486,11 +464,10 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_value = w * h / float(te[0]) / 1e6
         e2e_pinned = None
-        e2e_ok = bool(rank != 0 or np.array_equal(host_frame.reshape(h, w, 3), frame_host))
+        e2e_ok = bool(rank != 0 or np.array_equal(shm.image, frame_host))
         e2e_how = ("every rank copies its band over its own PCIe link into one pinned host frame shared by the ranks "
-                   f"(POSIX shared memory, cudaHostRegister rc {int(reg_rc[0]) if isinstance(reg_rc, tuple) else int(reg_rc)}, pinned {pinned}); "
+                   f"(POSIX shared memory, cudaHostRegister rc {reg_rc}, pinned {pinned}); "
                    f"frame equals the device-path frame: {e2e_ok}")
-        rt.cudaHostUnregister(host_frame.ctypes.data)
         barrier()
 
     # ---- the same split through ONE process: maray_cuda_create(N) from rank 0 (what a Rust host calls) ----
@@ -568,9 +545,8 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
                 rec["cpu_baseline"]["jit_standin"] = cpu_jit_standin(scene_bytes, textures, w, h, threads, stats["dag_nodes"])
     r.close()
     if shm is not None:
+        del host_band
         shm.close()
-        if rank == 0:
-            shm.unlink()
     return rec
 
 

@@ -1,9 +1,14 @@
-"""Row-band partition of an image over ranks / GPUs, and the band gather for one-process-per-GPU hosts.
+"""Row-band partition of an image over ranks / GPUs, and how the bands of one-process-per-GPU hosts meet.
 
 The reference schedules independent rows (rayon over 0..h, reference src/render.rs:85; a shared row
-counter, reference src/render.rs:150-173).  Here rank r owns the contiguous rows
-[band(h, n, r)), renders them on its own GPU, and the bands are gathered on rank 0 -- the only
-exchange step of the path.  `torch.distributed` is plumbing: NCCL on GPUs, gloo in the CPU tests.
+counter, reference src/render.rs:150-173).  Here rank r owns the contiguous rows [band(h, n, r)) and
+renders them on its own GPU.  Three ways for the bands to become one frame, all used by bench.py:
+  * device frame on rank 0, no gather: the band kernels store into rank 0's frame over NVLink
+    (CudaRenderer.frame_export / frame_import, CUDA IPC);
+  * host frame: every rank copies its band into ONE host frame shared by the ranks (SharedHostFrame:
+    POSIX shared memory, pinned by every rank), over its own PCIe link;
+  * gather_bands: one `gather` collective to rank 0 (NCCL on GPUs, gloo in the CPU tests).
+`torch.distributed` is plumbing throughout.
 """
 from __future__ import annotations
 
@@ -55,3 +60,75 @@ def gather_bands(band_buf, frame, w: int, h: int, rank: int, world: int, group=N
                 frame[y0 * w * 3: y1 * w * 3].copy_(pieces[r][: (y1 - y0) * w * 3])
     else:
         dist.gather(band_buf[:piece], None, dst=0, group=group)
+
+
+class SharedHostFrame:
+    """One h x w x 3 host image shared by the ranks of a one-process-per-GPU job: rank 0 creates a POSIX shared
+    memory segment, the others attach to it by name (passed through `torch.distributed`), and every rank copies
+    its own band into its own rows -- so a frame leaves N GPUs over N PCIe links instead of one.  `pin()` page-locks
+    the mapping in the calling process (cudaHostRegister) so the copies can be asynchronous."""
+
+    def __init__(self, w: int, h: int, rank: int, world: int, group=None):
+        import numpy as np
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+
+        self.w, self.h, self.rank = w, h, rank
+        box = [None]
+        if rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=max(1, h * w * 3))
+            box[0] = self._shm.name
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        if rank != 0:
+            self._shm = shared_memory.SharedMemory(name=box[0])
+            try:    # attaching registers the segment with this process's resource tracker, which would unlink it at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.flat = np.ndarray((h * w * 3,), dtype=np.uint8, buffer=self._shm.buf)
+        self._pinned = False
+
+    @property
+    def image(self):
+        return self.flat.reshape(self.h, self.w, 3)
+
+    def band_view(self, y0: int, y1: int):
+        """This rank's rows as a flat torch uint8 tensor over the shared memory."""
+        import torch
+        return torch.from_numpy(self.flat)[y0 * self.w * 3: y1 * self.w * 3]
+
+    def pin(self) -> int:
+        """cudaHostRegister of the mapping; returns the CUDA error code (0 = pinned)."""
+        import torch
+        rc = torch.cuda.cudart().cudaHostRegister(self.flat.ctypes.data, self.flat.nbytes, 0)
+        rc = int(rc[0]) if isinstance(rc, tuple) else int(rc)
+        self._pinned = rc == 0
+        return rc
+
+    def close(self) -> None:
+        import torch
+        if self._pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.flat.ctypes.data)
+            self._pinned = False
+        self.flat = None
+        self._shm.close()
+        if self.rank == 0:
+            self._shm.unlink()
+
+
+def host_barrier(tag: str, world: int) -> None:
+    """Barrier through the rendezvous store: the waiting ranks hold no GPU.  (An NCCL barrier parks a spinning
+    kernel on every waiting rank's GPU; when rank 0 then renders on ALL GPUs from one process -- the in-process
+    multi-GPU measurement of bench.py -- that kernel time-slices against rank 0's work.)"""
+    import time
+    import torch.distributed as dist
+
+    if world == 1:
+        return
+    store = dist.distributed_c10d._get_default_store()
+    key = f"maray_host_barrier_{tag}"
+    store.add(key, 1)
+    while int(store.add(key, 0)) < world:
+        time.sleep(0.002)

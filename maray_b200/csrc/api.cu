@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -452,10 +453,10 @@ int nvrtc_compile(JitBuild* jb, const std::atomic<bool>* cancel, bool cached_onl
 
 // Interpreter launch shape.  The per-thread slot file (n_wide * P * 8 bytes) bounds how many warps an SM
 // holds, and one bytecode instruction is a chain of dependent shared-memory, branch and FP64 latencies, so
-// throughput follows the number of pixels in flight per SM: resident warps x P (measured sweeps:
-// profiles/r02_interp_sweeps.md -- at equal product P = 2 is a little ahead of P = 1 and P = 4).  Blocks
-// of any multiple of 32 threads are considered: fewer, larger blocks spend less shared memory on the
-// per-block parts (instruction chunks, scalar file, staging tile) and so hold more warps.
+// throughput follows the number of pixels in flight per SM: resident warps x P, with diminishing returns
+// on both (measured sweeps: profiles/r02_interp_sweeps.md).  Blocks of any multiple of 32 threads are
+// considered: fewer, larger blocks spend less shared memory on the per-block parts (instruction chunks,
+// scalar file, staging tile) and so hold more warps.
 void choose_interp_shape(maray_cuda* h) {
     const unsigned n_scal = unsigned(h->bc.consts.size()) + h->bc.n_uniform;
     auto fits = [&](unsigned b, unsigned p) {
@@ -480,7 +481,9 @@ void choose_interp_shape(maray_cuda* h) {
             // lanes past the end of a row idle: count the row width the scene was authored for
             const unsigned span = b * p, sw = std::max<unsigned>(h->scene.size[0], 1);
             const double row_fill = double(sw) / (double((sw + span - 1) / span) * span);
-            const double score = warps * p * (p == 2 ? 1.0 : 0.95) * row_fill - 0.001 * b;
+            // measured (profiles/r02_interp_sweeps.md): throughput follows resident warps up to ~24 per SM, and
+            // P pixels per thread amortise the dispatch a little less than linearly
+            const double score = std::min(warps, 24.0) * std::pow(double(p), 0.85) * row_fill - 0.001 * b;
             if (score > best) { best = score; h->interp_block = b; h->interp_ppt = p; }
         }
 }

@@ -58,3 +58,35 @@ def test_gather_bands_gloo(world, h, tmp_path):
     out = str(tmp_path / "frame.npy")
     mp.spawn(_worker, args=(world, _free_port(), w, h, scene, out), nprocs=world, join=True)
     assert np.array_equal(np.load(out), OracleScene(scene).render(w, h))
+
+
+def _shared_frame_worker(rank, world, port, w, h, scene, out_path):
+    from oracle.oracle import OracleScene
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    frame = bands.SharedHostFrame(w, h, rank, world)
+    y0, y1 = bands.band(h, world, rank)
+    mine = OracleScene(scene).render_window(0, w, y0, y1, threads=1)
+    frame.band_view(y0, y1).copy_(torch.from_numpy(mine.reshape(-1)))      # every rank writes its own rows
+    bands.host_barrier("frame_written", world)                             # store-based: no collective, no device
+    if rank == 0:
+        np.save(out_path, np.array(frame.image))
+    bands.host_barrier("frame_read", world)
+    frame.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,h", [(2, 41), (3, 40)])
+def test_shared_host_frame_gloo(world, h, tmp_path):
+    """The end-to-end exchange of bench.py at N > 1: one host frame in POSIX shared memory, every rank fills in
+    its own band, a store-based barrier says when it is complete (on the GPU box the rows arrive by
+    device->host copies over each GPU's own PCIe link)."""
+    from oracle.oracle import OracleScene
+
+    w = 48
+    scene = scenes.sdf(w, h, 5, seed=4)
+    out = str(tmp_path / "frame.npy")
+    mp.spawn(_shared_frame_worker, args=(world, _free_port(), w, h, scene, out), nprocs=world, join=True)
+    assert np.array_equal(np.load(out), OracleScene(scene).render(w, h))

@@ -552,6 +552,36 @@ def test_auto_backend_first_frame_and_switch(monkeypatch, tmp_path):
         assert np.array_equal(r.render(1024, 1024), want)
 
 
+def test_frame_shared_between_processes_over_cuda_ipc(tmp_path):
+    """One process per GPU without a gather: the first process exports its device frame (CUDA IPC), a second
+    process opens it and renders its band straight into that memory.  (Both processes share the one GPU of the
+    test box; on the 8-GPU node the stores travel over NVLink -- bench.py --gpus N.)"""
+    import subprocess
+    import sys
+    scene = scenes.sdf(640, 360, 16, seed=2)
+    w, h, cut = 640, 360, 131
+    scene_path = tmp_path / "s.maray"
+    scene_path.write_bytes(scene)
+    with _renderer(scene, "nvrtc") as r:
+        want = r.render(w, h)
+        handle, frame = r.frame_export(w, h)
+        r.render_band(w, h, 0, cut, frame, 0)
+        child = (
+            "import sys; sys.path.insert(0, %r)\n"
+            "import numpy as np\n"
+            "from maray_b200 import CudaRenderer\n"
+            "r = CudaRenderer(gpus=1); r.load(open(%r, 'rb').read()); r.compile('nvrtc')\n"
+            "p = r.frame_import(bytes.fromhex(%r))\n"
+            "r.render_band(%d, %d, %d, %d, p + %d, 0)\n"
+            "probe = np.zeros(1, np.uint8); r.copy_to_host(p, probe)   # default-stream copy: the band kernel is done\n"
+            "r.close()\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(scene_path), handle.hex(), w, h, cut, h, cut * w * 3))
+        res = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        got = np.zeros((h, w, 3), dtype=np.uint8)
+        r.copy_to_host(frame, got)
+    assert np.array_equal(got, want)
+
+
 def test_multi_gpu_in_process_matches_single():
     import torch
     if torch.cuda.device_count() < 2:
