@@ -118,6 +118,17 @@ int maray_cuda_load_maray(maray_cuda_t* h, const uint8_t* bytes, size_t len);
 /* The [u32;2] size stored in the file. */
 int maray_cuda_scene_size(const maray_cuda_t* h, uint32_t* w, uint32_t* hgt);
 
+/* Which sin/exp/ln the device evaluates `Expr::Sin/Exp/Ln` with (reference src/lib.rs:648-650 calls the platform
+ * libm; src/wasm.rs:11-13 imports the same functions).  Takes effect at the next maray_cuda_compile.
+ *   MARAY_LIBM_FAST   the default: 15 / 17 / 30 FP64 instructions, <= 1.5 / 0.86 / 0.58 ULP -- equal to glibc's result
+ *                     in 84-99 % of arguments, one ULP away in the rest;
+ *   MARAY_LIBM_GLIBC  exact mode: glibc 2.39's own algorithms (x86-64 FMA variants) operation for operation, so every
+ *                     value has the bits the reference computes on such a host (|x| >= 105414350 in sin excepted);
+ *   MARAY_LIBM_CUDA   libdevice's sin/exp/log (A/B).
+ * The environment variable MARAY_LIBM=fast|glibc|cuda sets the default of new handles. */
+enum { MARAY_LIBM_FAST = 0, MARAY_LIBM_GLIBC = 1, MARAY_LIBM_CUDA = 2 };
+int maray_cuda_set_libm(maray_cuda_t* h, int libm);
+
 /* Lowers the scene (lexical Let, hash-consing across channels, host constant folding) and builds
  * the chosen back end.  Stands in for `var_fixer::fix_color` + `Wasm::from_expr` x3
  * (reference src/render.rs:117,163-165; src/wasm.rs:136-158).  `stats` may be NULL. */

@@ -12,6 +12,7 @@ OK, E_INVALID, E_PARSE, E_SCENE, E_COMPILE, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -
 BACKEND_INTERP, BACKEND_NVRTC, BACKEND_AUTO = 0, 1, 2
 REPORT_NONE, REPORT_ROW, REPORT_DURATION_MS = 0, 1, 2
 IPC_HANDLE_BYTES = 64
+LIBM_FAST, LIBM_GLIBC, LIBM_CUDA = 0, 1, 2
 
 REPORT_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_uint32, ctypes.c_uint32,
                              ctypes.c_double)
@@ -51,6 +52,7 @@ SYMBOLS = [
                                                ctypes.POINTER(ctypes.c_uint32)]),
     ("maray_cuda_load_maray", ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_size_t]),
     ("maray_cuda_scene_size", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
+    ("maray_cuda_set_libm", ctypes.c_int, [_P, ctypes.c_int]),
     ("maray_cuda_compile", ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(Stats)]),
     ("maray_cuda_set_report", ctypes.c_int, [_P, ctypes.c_int, ctypes.c_uint32, REPORT_FN, _P]),
     ("maray_cuda_render", ctypes.c_int, [_P, ctypes.c_uint32, ctypes.c_uint32, _P, ctypes.POINTER(Stats)]),

@@ -83,6 +83,7 @@ struct JitBuild {
     std::vector<std::vector<char>> cubins;    // one per unit
     CodegenInfo info;
     unsigned maxreg = 0;
+    int libm = MARAY_LIBM_FAST;               // which sin/exp/ln the units are compiled against (maray_cuda_set_libm)
     double codegen_ms = 0.0, nvrtc_ms = 0.0;
     uint32_t registers = 0, compile_threads = 0, cache_hit = 0;
     std::string error;
@@ -115,6 +116,7 @@ struct maray_cuda {
     Bytecode bc;
     std::vector<uint64_t> bc_device;                   // bc.code with operand fields scaled for the launch shape
     unsigned interp_block = 128, interp_ppt = 2;       // launch shape: threads per block, pixels per thread
+    int libm = MARAY_LIBM_FAST;                        // maray_cuda_set_libm / MARAY_LIBM
     int interp_dispatch = 0;                           // MARAY_INTERP_DISPATCH=tree (kernels.hpp launch_interp), A/B
     unsigned jit_block = 256;
     unsigned jit_dyn_smem = 0;                         // dynamic shared memory of the generated kernel
@@ -367,8 +369,8 @@ int nvrtc_compile(JitBuild* jb, const std::atomic<bool>* cancel, bool cached_onl
     if (lineinfo) options.push_back("-lineinfo");
     if (jb->maxreg) options.push_back("--maxrregcount=" + std::to_string(jb->maxreg));
     if (std::getenv("MARAY_JIT_NOSLOW")) options.push_back("-DMR_NO_SLOW=1");   // experiment only (wrong for huge/NaN arguments)
-    if (const char* e = std::getenv("MARAY_LIBM"))      // A/B: MARAY_LIBM=cuda uses libdevice's sin/exp/log
-        if (std::string(e) == "cuda") options.push_back("-DMR_LIBM_PLAIN=1");
+    if (jb->libm == MARAY_LIBM_CUDA) options.push_back("-DMR_LIBM_PLAIN=1");    // A/B: libdevice's sin/exp/log
+    if (jb->libm == MARAY_LIBM_GLIBC) options.push_back("-DMR_LIBM_GLIBC=1");   // exact mode (device_libm_glibc.cuh)
 
     jb->registers = 0;
     jb->compile_threads = 0;
@@ -495,6 +497,9 @@ void choose_interp_shape(maray_cuda* h) {
 int jit_build(const Program& prog, JitBuild* jb, bool cached_only, const std::atomic<bool>* cancel) {
     double t1 = now_ms();
     CodegenOptions copt;
+    // Exact mode: the routines branch on ranges and read tables -- always out of line (inlined, chess.maray's 256 sines
+    // are 5.7 MB of code and 53 s of NVRTC here instead of 1.7 MB / 11 s).
+    if (jb->libm == MARAY_LIBM_GLIBC) copt.inline_transcendentals_below = 0;
     if (const char* e = std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = uint32_t(std::strtoul(e, nullptr, 10));
     if (const char* e = std::getenv("MARAY_JIT_INLINE_TRANS_BELOW")) copt.inline_transcendentals_below = uint32_t(std::strtoul(e, nullptr, 10));
     if (const char* e = std::getenv("MARAY_JIT_SYNC_EVERY")) copt.sync_every = uint32_t(std::strtoul(e, nullptr, 10));
@@ -730,6 +735,7 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
             t.tex = g.d_textab;
             t.x0 = x; t.x1 = x + cols; t.y0 = y; t.rows = rows; t.nxb = 0;
             t.out_aligned = (reinterpret_cast<uintptr_t>(t.out) % 16 == 0) ? 1u : 0u;
+            t.libm_exact = h->libm == MARAY_LIBM_GLIBC ? 1u : 0u;
             CU_TRY(h, launch_interp(t, g.d_code, unsigned(h->bc_device.size()), g.d_consts, unsigned(h->bc.consts.size()),
                                     h->bc.n_uniform, h->bc.n_wide, !h->bc.row_uniform, h->interp_block, h->interp_ppt, stream,
                                     h->interp_dispatch));
@@ -986,6 +992,10 @@ int maray_cuda_create(int n_gpus, const int* device_ids, maray_cuda_t** out) {
     if (!out || n_gpus < 0) return fail(nullptr, MARAY_E_INVALID, "maray_cuda_create: bad arguments");
     *out = nullptr;
     std::unique_ptr<maray_cuda> h(new maray_cuda());
+    if (const char* e = std::getenv("MARAY_LIBM")) {
+        const std::string v(e);
+        h->libm = v == "glibc" ? MARAY_LIBM_GLIBC : v == "cuda" ? MARAY_LIBM_CUDA : MARAY_LIBM_FAST;
+    }
     if (n_gpus > 0) {
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
@@ -1114,6 +1124,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         rc = interp_build_and_install(h);
     } else if (backend == MARAY_BACKEND_NVRTC) {
         JitBuild jb;
+        jb.libm = h->libm;
         rc = jit_build(h->prog, &jb, /*cached_only=*/false, nullptr);
         if (rc) { h->jit = std::move(jb); fill_jit_stats(h); return fail(h, rc, h->jit.error); }   // the generated text stays inspectable
         rc = jit_install(h, std::move(jb));
@@ -1122,6 +1133,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         // ready in milliseconds -- renders while NVRTC works on another thread; renders switch to the generated
         // kernels, between row chunks, as soon as they are built.  Both back ends produce the same bytes.
         JitBuild jb;
+        jb.libm = h->libm;
         rc = jit_build(h->prog, &jb, /*cached_only=*/true, nullptr);
         if (rc == MARAY_OK) {
             rc = jit_install(h, std::move(jb));
@@ -1130,6 +1142,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
             if (rc == MARAY_E_UNSUPPORTED) {
                 // the slot file does not fit: compile now, there is nothing to render with meanwhile
                 JitBuild now;
+                now.libm = h->libm;
                 rc = jit_build(h->prog, &now, false, nullptr);
                 if (rc) return fail(h, rc, now.error);
                 rc = jit_install(h, std::move(now));
@@ -1137,6 +1150,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
                 h->job.reset(new JitJob());
                 JitJob* job = h->job.get();
                 job->prog = h->prog;
+                job->build.libm = h->libm;
                 job->th = std::thread([job] {
                     job->rc = jit_build(job->prog, &job->build, false, &job->cancel);
                     job->state = job->rc == MARAY_OK ? 1 : 2;
@@ -1147,6 +1161,12 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
     if (rc) return rc;
     h->compiled = true;
     if (stats) *stats = h->stats;
+    return MARAY_OK;
+}
+
+int maray_cuda_set_libm(maray_cuda_t* h, int libm) {
+    if (!h || libm < MARAY_LIBM_FAST || libm > MARAY_LIBM_CUDA) return fail(h, MARAY_E_INVALID, "maray_cuda_set_libm: bad libm");
+    h->libm = libm;
     return MARAY_OK;
 }
 

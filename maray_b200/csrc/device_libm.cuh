@@ -72,9 +72,9 @@ static inline double mr_hilo(int hi, int lo) {
     uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double d; memcpy(&d, &u, 8); return d;
 }
 static inline double mr_rcp_approx(double b) { return (double)(1.0f / (float)b); }   // >= 20 good bits, like MUFU.RCP64H
-#define MR_SLOW_SIN(x) sin(x)
-#define MR_SLOW_EXP(x) exp(x)
-#define MR_SLOW_LOG(x) log(x)
+#define MR_SLOW_SIN_F(x) sin(x)
+#define MR_SLOW_EXP_F(x) exp(x)
+#define MR_SLOW_LOG_F(x) log(x)
 #define MR_LDG2(p, lo, hi) do { (lo) = (p)[0]; (hi) = (p)[1]; } while (0)
 #else
 #define MR_FN __device__ __forceinline__
@@ -92,10 +92,14 @@ __device__ __forceinline__ double mr_rcp_approx(double b) {
 static __device__ __noinline__ double mr_slow_sin(double x) { return sin(x); }
 static __device__ __noinline__ double mr_slow_exp(double x) { return exp(x); }
 static __device__ __noinline__ double mr_slow_log(double x) { return log(x); }
-#define MR_SLOW_SIN(x) mr_slow_sin(x)
-#define MR_SLOW_EXP(x) mr_slow_exp(x)
-#define MR_SLOW_LOG(x) mr_slow_log(x)
+#define MR_SLOW_SIN_F(x) mr_slow_sin(x)
+#define MR_SLOW_EXP_F(x) mr_slow_exp(x)
+#define MR_SLOW_LOG_F(x) mr_slow_log(x)
 #define MR_LDG2(p, lo, hi) do { double2 v2_ = __ldg(reinterpret_cast<const double2*>(p)); (lo) = v2_.x; (hi) = v2_.y; } while (0)
+#endif
+
+#if defined(MR_LIBM_GLIBC) || defined(MR_LIBM_BOTH) || defined(MR_LIBM_HOST)
+#include "device_libm_glibc.cuh"   // exact mode: mr_*_inrange_g, mr_*_fast_g, mr_*_slow_g
 #endif
 
 // Constants, read as constant-bank operands.
@@ -139,12 +143,12 @@ static __device__ __align__(16) const double MR_SINCOS[2][6] = {
 // parity.  Everything else (incl. NaN, infinity) goes to libdevice.
 // The range tests look at the high word only (integer pipe, not the FP64 pipe); NaN and infinity
 // have a high word above every bound, so they always take the libdevice branch.
-MR_FN int mr_sin_inrange(double x) { return (unsigned int)(mr_hi32(x) & 0x7fffffff) < 0x41500000u; }   // |x| < 2^22
-MR_FN int mr_exp_inrange(double x) { return (unsigned int)(mr_hi32(x) & 0x7fffffff) < 0x40862000u; }   // |x| < 708
-MR_FN int mr_log_inrange(double x) { return (unsigned int)(mr_hi32(x) - 0x00100000) < 0x7fe00000u; }   // positive normal
+MR_FN int mr_sin_inrange_f(double x) { return (unsigned int)(mr_hi32(x) & 0x7fffffff) < 0x41500000u; }   // |x| < 2^22
+MR_FN int mr_exp_inrange_f(double x) { return (unsigned int)(mr_hi32(x) & 0x7fffffff) < 0x40862000u; }   // |x| < 708
+MR_FN int mr_log_inrange_f(double x) { return (unsigned int)(mr_hi32(x) - 0x00100000) < 0x7fe00000u; }   // positive normal
 
 // Straight-line fast paths: safe (no traps, no loops) for ANY argument, meaningful inside the range.
-MR_FN double mr_sin_fast(double x) {
+MR_FN double mr_sin_fast_f(double x) {
     const double t = MR_FMA(x, MR_LK[1], MR_LK[0]);
     const double q = t - MR_LK[0];
     double r = MR_FMA(q, -MR_LK[2], x);
@@ -170,24 +174,10 @@ MR_FN double mr_sin_fast(double x) {
     const double v = odd ? p : sn;
     return mr_hilo((int)((unsigned int)mr_hi32(v) ^ (((unsigned int)qi & 2u) << 30)), mr_lo32(v));   // quadrants 2,3: negate
 }
-// Two shapes, measured: inlined into straight-line code the "compute, then repair" form is faster
-// (chess_4k 7.80 vs 8.19 ms); inside the out-of-line batched helpers the early-out form is
-// (deep scene 20.0 vs 23.6 ms: nothing but x is live across the libdevice call).
-MR_FN double mr_sin(double x) {
-    double r = mr_sin_fast(x);
-#ifndef MR_NO_SLOW   /* experiment only: measures what the out-of-range branches cost */
-    if (MR_UNLIKELY(!mr_sin_inrange(x))) r = MR_SLOW_SIN(x);
-#endif
-    return r;
-}
-MR_FN double mr_sin_eo(double x) {
-    if (!mr_sin_inrange(x)) return MR_SLOW_SIN(x);
-    return mr_sin_fast(x);
-}
 
 // exp(x).  Fast range |x| < 708: n = rint(x*log2(e)), r = x - n*ln2 (two FMAs), degree-12 polynomial,
 // scaling by 2^n through the exponent field.
-MR_FN double mr_exp_fast(double x) {
+MR_FN double mr_exp_fast_f(double x) {
     const double t = MR_FMA(x, MR_LK[5], MR_LK[0]);
     const double n = t - MR_LK[0];
     double r = MR_FMA(n, -MR_LK[6], x);
@@ -207,26 +197,12 @@ MR_FN double mr_exp_fast(double x) {
     p = MR_FMA(p, r, 1.0);
     return mr_hilo((int)((unsigned int)mr_hi32(p) + ((unsigned int)mr_lo32(t) << 20)), mr_lo32(p));
 }
-// Two shapes, measured: inlined into straight-line code the "compute, then repair" form is faster
-// (chess_4k 7.80 vs 8.19 ms); inside the out-of-line batched helpers the early-out form is
-// (deep scene 20.0 vs 23.6 ms: nothing but x is live across the libdevice call).
-MR_FN double mr_exp(double x) {
-    double r = mr_exp_fast(x);
-#ifndef MR_NO_SLOW   /* experiment only: measures what the out-of-range branches cost */
-    if (MR_UNLIKELY(!mr_exp_inrange(x))) r = MR_SLOW_EXP(x);
-#endif
-    return r;
-}
-MR_FN double mr_exp_eo(double x) {
-    if (!mr_exp_inrange(x)) return MR_SLOW_EXP(x);
-    return mr_exp_fast(x);
-}
 
 // log(x).  Fast range: positive normal finite x.  x = m * 2^e with m in [sqrt(1/2), sqrt(2));
 // u = 2(m-1)/(m+1) from an approximate reciprocal refined by two Newton steps, with the exact
 // remainder of that division carried as u_lo; log(m) = u + u_lo + u^3*Q(u^2); the sum with e*ln2
 // is compensated.
-MR_FN double mr_log_fast(double x) {
+MR_FN double mr_log_fast_f(double x) {
     const int hx = mr_hi32(x);
     int e = (hx >> 20) - 1023;
     int mh = (hx & 0x000fffff) | 0x3ff00000;
@@ -259,15 +235,81 @@ MR_FN double mr_log_fast(double x) {
     const double lo = MR_FMA(ed, MR_LK[7], t3) + c;
     return h + lo;
 }
+
+
+// Which implementation the names below mean.  Default: the fast versions above.  MR_LIBM_GLIBC (MARAY_LIBM=glibc):
+// the exact mode of device_libm_glibc.cuh.  MR_LIBM_BOTH (the interpreter kernel, which is compiled ahead of time and
+// switches at run time): fast under the plain names, exact as mr_sin_g / mr_exp_g / mr_log_g.
+#ifdef MR_LIBM_GLIBC
+#define MR_SEL(name) name##_g
+#define MR_SLOW_SIN(x) mr_sin_slow_g(x)
+#define MR_SLOW_EXP(x) mr_exp_slow_g(x)
+#define MR_SLOW_LOG(x) mr_log_slow_g(x)
+#else
+#define MR_SEL(name) name##_f
+#define MR_SLOW_SIN(x) MR_SLOW_SIN_F(x)
+#define MR_SLOW_EXP(x) MR_SLOW_EXP_F(x)
+#define MR_SLOW_LOG(x) MR_SLOW_LOG_F(x)
+#endif
+#define MR_DEFINE_SELECTED(fn)                                                          \
+    MR_FN int mr_##fn##_inrange(double x) { return MR_SEL(mr_##fn##_inrange)(x); }      \
+    MR_FN double mr_##fn##_fast(double x) { return MR_SEL(mr_##fn##_fast)(x); }
+MR_DEFINE_SELECTED(sin)
+MR_DEFINE_SELECTED(exp)
+MR_DEFINE_SELECTED(log)
+#if defined(MR_LIBM_GLIBC) || defined(MR_LIBM_BOTH) || defined(MR_LIBM_HOST)
+MR_FN double mr_sin_g(double x) { return mr_sin_inrange_g(x) ? mr_sin_fast_g(x) : mr_sin_slow_g(x); }
+MR_FN double mr_exp_g(double x) { return mr_exp_inrange_g(x) ? mr_exp_fast_g(x) : mr_exp_slow_g(x); }
+MR_FN double mr_log_g(double x) { return mr_log_inrange_g(x) ? mr_log_fast_g(x) : mr_log_slow_g(x); }
+#endif
+
 // Two shapes, measured: inlined into straight-line code the "compute, then repair" form is faster
 // (chess_4k 7.80 vs 8.19 ms); inside the out-of-line batched helpers the early-out form is
 // (deep scene 20.0 vs 23.6 ms: nothing but x is live across the libdevice call).
+MR_FN double mr_sin(double x) {
+#ifdef MR_LIBM_GLIBC
+    if (MR_UNLIKELY(!mr_sin_inrange(x))) return MR_SLOW_SIN(x);
+    return mr_sin_fast(x);
+#else
+    double r = mr_sin_fast(x);
+#ifndef MR_NO_SLOW   /* experiment only: measures what the out-of-range branches cost */
+    if (MR_UNLIKELY(!mr_sin_inrange(x))) r = MR_SLOW_SIN(x);
+#endif
+    return r;
+#endif
+}
+MR_FN double mr_sin_eo(double x) {
+    if (!mr_sin_inrange(x)) return MR_SLOW_SIN(x);
+    return mr_sin_fast(x);
+}
+
+MR_FN double mr_exp(double x) {
+#ifdef MR_LIBM_GLIBC
+    if (MR_UNLIKELY(!mr_exp_inrange(x))) return MR_SLOW_EXP(x);
+    return mr_exp_fast(x);
+#else
+    double r = mr_exp_fast(x);
+#ifndef MR_NO_SLOW   /* experiment only: measures what the out-of-range branches cost */
+    if (MR_UNLIKELY(!mr_exp_inrange(x))) r = MR_SLOW_EXP(x);
+#endif
+    return r;
+#endif
+}
+MR_FN double mr_exp_eo(double x) {
+    if (!mr_exp_inrange(x)) return MR_SLOW_EXP(x);
+    return mr_exp_fast(x);
+}
 MR_FN double mr_log(double x) {
+#ifdef MR_LIBM_GLIBC
+    if (MR_UNLIKELY(!mr_log_inrange(x))) return MR_SLOW_LOG(x);
+    return mr_log_fast(x);
+#else
     double r = mr_log_fast(x);
 #ifndef MR_NO_SLOW   /* experiment only: measures what the out-of-range branches cost */
     if (MR_UNLIKELY(!mr_log_inrange(x))) r = MR_SLOW_LOG(x);
 #endif
     return r;
+#endif
 }
 MR_FN double mr_log_eo(double x) {
     if (!mr_log_inrange(x)) return MR_SLOW_LOG(x);
@@ -315,7 +357,7 @@ extern __shared__ double mr_dyn_f64[];
 // (Left to itself the compiler emits one whole chain after the other -- measured: 47 % of the helpers'
 // cycles were fixed-latency waits on the previous DFMA with 4 warps per scheduler.)  Same operations in
 // the same order per lane as mr_sin_fast / mr_exp_fast / mr_log_fast: bit-identical results.
-__device__ __forceinline__ void mr_sin_fast_w(const double* x, double* out) {
+__device__ __forceinline__ void mr_sin_fast_w_f(const double* x, double* out) {
     double t[MR_W], q[MR_W], r[MR_W], s[MR_W], p[MR_W], k[MR_W][6], sn[MR_W];
     int qi[MR_W], odd[MR_W];
     MR_EACH t[i] = MR_FMA(x[i], MR_LK[1], MR_LK[0]);
@@ -345,7 +387,7 @@ __device__ __forceinline__ void mr_sin_fast_w(const double* x, double* out) {
         out[i] = mr_hilo((int)((unsigned int)mr_hi32(v) ^ (((unsigned int)qi[i] & 2u) << 30)), mr_lo32(v));
     }
 }
-__device__ __forceinline__ void mr_exp_fast_w(const double* x, double* out) {
+__device__ __forceinline__ void mr_exp_fast_w_f(const double* x, double* out) {
     double t[MR_W], n[MR_W], r[MR_W], p[MR_W];
     MR_EACH t[i] = MR_FMA(x[i], MR_LK[5], MR_LK[0]);
     MR_EACH n[i] = t[i] - MR_LK[0];
@@ -366,7 +408,7 @@ __device__ __forceinline__ void mr_exp_fast_w(const double* x, double* out) {
     MR_EACH p[i] = MR_FMA(p[i], r[i], 1.0);
     MR_EACH out[i] = mr_hilo((int)((unsigned int)mr_hi32(p[i]) + ((unsigned int)mr_lo32(t[i]) << 20)), mr_lo32(p[i]));
 }
-__device__ __forceinline__ void mr_log_fast_w(const double* x, double* out) {
+__device__ __forceinline__ void mr_log_fast_w_f(const double* x, double* out) {
     double m[MR_W], a[MR_W], b[MR_W], y[MR_W], er[MR_W], u[MR_W], d[MR_W], rem[MR_W], u_lo[MR_W], w[MR_W], Q[MR_W];
     double t3[MR_W], ed[MR_W], h[MR_W], c[MR_W], lo[MR_W];
     MR_EACH {
@@ -402,6 +444,15 @@ __device__ __forceinline__ void mr_log_fast_w(const double* x, double* out) {
     MR_EACH lo[i] = MR_FMA(ed[i], MR_LK[7], t3[i]) + c[i];
     MR_EACH out[i] = h[i] + lo[i];
 }
+#ifdef MR_LIBM_GLIBC
+// The exact mode branches inside an evaluation (ranges of sin, the near-1 path of log), so it is not written step-major.
+#define MR_DEFINE_FAST_W(fn) __device__ __forceinline__ void mr_##fn##_fast_w(const double* x, double* out) { MR_EACH out[i] = mr_##fn##_fast_g(x[i]); }
+#else
+#define MR_DEFINE_FAST_W(fn) __device__ __forceinline__ void mr_##fn##_fast_w(const double* x, double* out) { mr_##fn##_fast_w_f(x, out); }
+#endif
+MR_DEFINE_FAST_W(sin)
+MR_DEFINE_FAST_W(exp)
+MR_DEFINE_FAST_W(log)
 // Rows 0..7 of the scratch hold the arguments and are left intact; results go to rows 8..15
 // (MR_R(k)).  The helper returns one flag, "some argument was outside the fast range", and mr_*_fix
 // then recomputes exactly those rows with libdevice: no per-lane mask, no selects on the stores.

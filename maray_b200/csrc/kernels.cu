@@ -9,6 +9,7 @@
 #include <cstdint>
 
 #include "bytecode.hpp"
+#define MR_LIBM_BOTH 1   // fast libm under the plain names, the exact mode (glibc's bits) as mr_*_g: chosen at run time
 #include "device_sem.cuh"
 #include "interp_dispatch.inc"   // generated: tools/gen_interp_dispatch.py (jump-table dispatch + hot bodies, inline PTX)
 #include "kernels.hpp"
@@ -116,6 +117,14 @@ struct OpStep { static __device__ __forceinline__ double f(double x) { return mr
 struct OpSin { static __device__ __forceinline__ double f(double x) { return mr_sin(x); } };
 struct OpExp { static __device__ __forceinline__ double f(double x) { return mr_exp(x); } };
 struct OpLn { static __device__ __forceinline__ double f(double x) { return mr_log(x); } };
+// Exact mode (MrTileParams::libm_exact, device_libm_glibc.cuh): out of line, so the default path's code and
+// registers are what they were.
+static __device__ __noinline__ double mr_sin_exact(double x) { return mr_sin_g(x); }
+static __device__ __noinline__ double mr_exp_exact(double x) { return mr_exp_g(x); }
+static __device__ __noinline__ double mr_log_exact(double x) { return mr_log_g(x); }
+struct OpSinX { static __device__ __forceinline__ double f(double x) { return mr_sin_exact(x); } };
+struct OpExpX { static __device__ __forceinline__ double f(double x) { return mr_exp_exact(x); } };
+struct OpLnX { static __device__ __forceinline__ double f(double x) { return mr_log_exact(x); } };
 
 template <int P, int KA, int KB, class Op>
 __device__ __forceinline__ void mr_bin(const Files<P>& f, double (&acc)[P], double sacc, unsigned int a, unsigned int b) {
@@ -150,6 +159,11 @@ __device__ __forceinline__ void mr_un(const Files<P>& f, double (&acc)[P], doubl
     case BC_H_UN + (U) * 4 + 1: mr_un<P, 1, OP>(F, acc, sacc, a); break;                                      \
     case BC_H_UN + (U) * 4 + 2: mr_un<P, 2, OP>(F, acc, sacc, a); break;                                      \
     case BC_H_UN + (U) * 4 + 3: mr_un<P, 3, OP>(F, acc, sacc, a); break;
+#define MR_UN_CASES_LIBM(U, OP, OPX)                                                                         \
+    case BC_H_UN + (U) * 4 + 0: if (exact) mr_un<P, 0, OPX>(F, acc, sacc, a); else mr_un<P, 0, OP>(F, acc, sacc, a); break; \
+    case BC_H_UN + (U) * 4 + 1: if (exact) mr_un<P, 1, OPX>(F, acc, sacc, a); else mr_un<P, 1, OP>(F, acc, sacc, a); break; \
+    case BC_H_UN + (U) * 4 + 2: if (exact) mr_un<P, 2, OPX>(F, acc, sacc, a); else mr_un<P, 2, OP>(F, acc, sacc, a); break; \
+    case BC_H_UN + (U) * 4 + 3: if (exact) mr_un<P, 3, OPX>(F, acc, sacc, a); else mr_un<P, 3, OP>(F, acc, sacc, a); break;
 #define MR_OUT_CASES(C)                                                                                      \
     case BC_H_OUT + (C) * 4 + 0: { double x[P]; mr_fetch<P, 0>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break; \
     case BC_H_OUT + (C) * 4 + 1: { double x[P]; mr_fetch<P, 1>(F, acc, sacc, a, x); F.store(out16 + (C) * slot16, x); } break; \
@@ -178,6 +192,8 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
     const unsigned int sbase_s = (unsigned int)__cvta_generic_to_shared(scal);
     const unsigned int slot16 = P * B / 2u;              // one wide slot in 16-byte units
     const unsigned int out16 = n_wide * slot16;          // the three channel slots follow the program's slots
+
+    const bool exact = p.libm_exact != 0u;
 
     const unsigned int row = blockIdx.x / p.nxb;
     const unsigned int xb = blockIdx.x - row * p.nxb;
@@ -244,9 +260,9 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
                     MR_UN_CASES(2, OpRecip)
                     MR_UN_CASES(3, OpSqrt)
                     MR_UN_CASES(4, OpStep)
-                    MR_UN_CASES(5, OpSin)
-                    MR_UN_CASES(6, OpExp)
-                    MR_UN_CASES(7, OpLn)
+                    MR_UN_CASES_LIBM(5, OpSin, OpSinX)
+                    MR_UN_CASES_LIBM(6, OpExp, OpExpX)
+                    MR_UN_CASES_LIBM(7, OpLn, OpLnX)
                     MR_UN_CASES(8, OpMov)
                     MR_OUT_CASES(0)
                     MR_OUT_CASES(1)
@@ -299,9 +315,9 @@ __global__ void __launch_bounds__(512) maray_interp(const MrTileParams p, const 
                 case BC_RECIP: sacc = mr_recip(x); break;
                 case BC_SQRT: sacc = mr_sqrt(x); break;
                 case BC_STEP: sacc = mr_step(x); break;
-                case BC_SIN: sacc = mr_sin(x); break;
-                case BC_EXP: sacc = mr_exp(x); break;
-                case BC_LN: sacc = mr_log(x); break;
+                case BC_SIN: sacc = exact ? mr_sin_exact(x) : mr_sin(x); break;
+                case BC_EXP: sacc = exact ? mr_exp_exact(x) : mr_exp(x); break;
+                case BC_LN: sacc = exact ? mr_log_exact(x) : mr_log(x); break;
                 case BC_TEX: {
                     const unsigned int imm = lo >> 16;
                     const MrTexture t = p.tex[imm >> 2];

@@ -19,6 +19,7 @@ struct MrTileParams {
     unsigned int x0, x1, y0, rows;
     unsigned int nxb;              // blocks per row (set by launch_interp)
     unsigned int out_aligned;      // out is 16-byte aligned: full, aligned blocks store uint4
+    unsigned int libm_exact;       // 1: sin/exp/ln return glibc's bits (device_libm_glibc.cuh, MARAY_LIBM=glibc)
 };
 
 namespace maray {

@@ -142,7 +142,14 @@ class CudaRenderer:
         self.size = (w.value, h.value)
         return self.size
 
-    def compile(self, backend: str = "nvrtc") -> dict:
+    def set_libm(self, libm: str) -> None:
+        """"fast" (default), "glibc" (exact mode: the bits of the host libm the reference calls, reference
+        src/lib.rs:648-650) or "cuda" (libdevice).  Takes effect at the next compile."""
+        self._check(self._L.maray_cuda_set_libm(self._h, {"fast": _lib.LIBM_FAST, "glibc": _lib.LIBM_GLIBC, "cuda": _lib.LIBM_CUDA}[libm]))
+
+    def compile(self, backend: str = "nvrtc", libm: Optional[str] = None) -> dict:
+        if libm is not None:
+            self.set_libm(libm)
         st = _lib.Stats()
         self._check(self._L.maray_cuda_compile(self._h, _BACKENDS[backend], ctypes.byref(st)))
         return st.as_dict()
