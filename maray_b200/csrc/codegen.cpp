@@ -47,6 +47,9 @@ struct Emitter {
     // Values that are exactly +0.0 or 1.0 at every pixel (see find_booleans): kind 1 = boolean,
     // kind 2 = the NOT pattern `1 + -(b)`.  Emitted as `bool` logic plus a double shadow.
     const std::vector<uint8_t>* boolean = nullptr;
+    // Sines that are only ever asked for their sign (see find_sign_only_sines): never materialised.
+    const std::vector<uint8_t>* sign_only = nullptr;
+    bool is_sign_only(uint32_t id) const { return sign_only && (*sign_only)[id]; }
 
     bool is_bool(uint32_t id) const { return boolean && (*boolean)[id]; }
     void bool_operand(std::string& s, uint32_t id) const {
@@ -127,6 +130,7 @@ struct Emitter {
     void statement(std::string& s, uint32_t id) const {
         const Node& n = P.nodes[id];
         if (n.op == OP_X || n.op == OP_Y) return;   // kernel arguments
+        if (is_sign_only(id)) return;               // its one consumer, a step, evaluates mr_sin_ge0 of the argument
         char buf[160];
         if (load_kind && (*load_kind)[id]) {
             if ((*load_kind)[id] == 1) std::snprintf(buf, sizeof buf, "  const double v%u = __ldg(CV + %uu * CW);\n", id, (*table_index)[id]);
@@ -141,7 +145,10 @@ struct Emitter {
             std::snprintf(buf, sizeof buf, "  const bool b%u = ", id);
             s += buf;
             switch (n.op) {
-            case OP_STEP: s += "("; operand(s, n.a); s += " >= 0.0)"; break;          // NaN -> false, -0.0 -> true
+            case OP_STEP:
+                if (is_sign_only(n.a)) { s += "mr_sin_ge0("; operand(s, P.nodes[n.a].a); s += ")"; }   // step(sin(u)): the sign is enough
+                else { s += "("; operand(s, n.a); s += " >= 0.0)"; }                  // NaN -> false, -0.0 -> true
+                break;
             case OP_ADD: {                                                           // 1 + -(b)  ==  !b
                 const uint32_t neg = P.nodes[n.a].op == OP_NEG ? n.a : n.b;
                 s += "!"; bool_operand(s, P.nodes[neg].a);
@@ -214,6 +221,27 @@ std::vector<uint8_t> find_booleans(const Program& prog) {
         }
     }
     return kind;
+}
+
+// step(sin(u)) where nothing else reads the sine -- Maray's `chess` is made of these (reference src/lib.rs:969-973) --
+// only needs the SIGN of the sine, which the argument reduction already decides: the polynomial, its table loads and
+// the quadrant selects are skipped (device_libm.cuh mr_sin_ge0; per sine 6 FP64 instructions instead of 16).  Exact:
+// mr_sin_ge0(u) == (mr_sin(u) >= 0.0) for every u, so no pixel changes.
+std::vector<uint8_t> find_sign_only_sines(const Program& prog, const std::vector<uint8_t>& booleans) {
+    const size_t n = prog.nodes.size();
+    std::vector<uint32_t> uses(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        const Node& nd = prog.nodes[i];
+        if (op_is_unary(nd.op) || op_is_binary(nd.op)) uses[nd.a]++;
+        if (op_is_binary(nd.op)) uses[nd.b]++;
+    }
+    for (int c = 0; c < 3; c++) uses[prog.root[c]]++;
+    std::vector<uint8_t> mark(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        const Node& nd = prog.nodes[i];
+        if (nd.op == OP_STEP && booleans[i] && prog.nodes[nd.a].op == OP_SIN && uses[nd.a] == 1) mark[nd.a] = 1;
+    }
+    return mark;
 }
 
 // Common generator.  Three forms:
@@ -325,6 +353,14 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         const uint32_t neg = prog.nodes[n.a].op == OP_NEG ? n.a : n.b;
         return prog.nodes[neg].a;
     };
+    // sign-only sines: unsegmented, unhoisted programs whose sines are not batched (the straight-line form)
+    std::vector<uint8_t> sign_only;
+    if (opt.boolean_logic && opt.sign_of_sine && !segmented && !hoist) {
+        sign_only = find_sign_only_sines(prog, booleans);
+        for (size_t i = 0; i < order.size(); i++)
+            if (order_batch[i] && sign_only[order[i]]) sign_only[order[i]] = 0;
+        em.sign_only = &sign_only;
+    }
     Emitter em_pre = em;                       // prologue kernels compute hoisted values, never load them
     if (hoist) { em.load_kind = &load_kind; em.table_index = &table_index; }
 

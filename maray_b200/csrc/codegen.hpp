@@ -37,6 +37,9 @@ struct CodegenOptions {
     // pixel cost more issue slots and exposed latency than the 1 227 mostly one-instruction values
     // they replace.  Kept as MARAY_JIT_HOIST=1 for scenes with expensive x-only/y-only sub-programs.
     bool hoist = false;
+    // step(sin(u)) with no other reader of the sine evaluates only the sign of the sine (mr_sin_ge0): exact, and on
+    // chess.maray a quarter of all instructions (MARAY_JIT_SIGN_OF_SINE=0 for A/B).
+    bool sign_of_sine = true;
     // Programs above segment_values: one KERNEL per segment, each its own translation unit, values that cross
     // a cut in a global-memory frame F[slot * FS + pixel].  The units share nothing: NVRTC compiles them
     // concurrently, nothing is linked, no segment pays a call ABI.  false = __noinline__ segment functions in

@@ -22,6 +22,7 @@
 MR_PLAIN_FN double mr_sin(double x) { return sin(x); }
 MR_PLAIN_FN double mr_exp(double x) { return exp(x); }
 MR_PLAIN_FN double mr_log(double x) { return log(x); }
+MR_PLAIN_FN int mr_sin_ge0(double x) { return sin(x) >= 0.0; }
 struct MrD2 { double a, b; };
 struct MrD4 { double a, b, c, d; };
 #define MR_DEFINE_BATCHED(fn)                                                                                   \
@@ -314,6 +315,35 @@ MR_FN double mr_log(double x) {
 MR_FN double mr_log_eo(double x) {
     if (!mr_log_inrange(x)) return MR_SLOW_LOG(x);
     return mr_log_fast(x);
+}
+
+// mr_sin(x) >= 0.0 without the sine: what `step(sin(u))` needs (Maray's `chess`, reference src/lib.rs:969-973).
+// The reduction x = q*pi/2 + r is the one of mr_sin_fast_f; in an even quadrant the value is +-(r + r*P) = +-r*(1 + P)
+// with |P| < 0.11, which has the sign of +-r (and is +-0 exactly when r is), in an odd quadrant it is +-(1 + s*C(s))
+// with the cosine in [0.7, 1].  The sign of the sine of a nonzero double is never in doubt at this accuracy, so the
+// same answer holds for glibc's sine (exact mode) as for the fast one.  Outside |x| < 2^22: the full routine.
+MR_FN int mr_sin_ge0_fast(double x) {
+    const double t = MR_FMA(x, MR_LK[1], MR_LK[0]);
+    const double q = t - MR_LK[0];
+    double r = MR_FMA(q, -MR_LK[2], x);
+    r = MR_FMA(q, -MR_LK[3], r);
+    r = MR_FMA(q, -MR_LK[4], r);
+    const unsigned int qi = (unsigned int)mr_lo32(t);
+    // One compare decides, without a branch: of +-r in the even quadrants, of +-1.x (the cosine's sign) in the odd ones.
+    const unsigned int hi = (qi & 1u) ? 0x3ff00000u : (unsigned int)mr_hi32(r);
+    return mr_hilo((int)(hi ^ ((qi & 2u) << 30)), mr_lo32(r)) >= 0.0;
+}
+#ifdef MR_LIBM_HOST
+static int mr_sin_ge0_slow(double x) { return mr_sin_eo(x) >= 0.0; }
+#else
+static __device__ __noinline__ int mr_sin_ge0_slow(double x) { return mr_sin_eo(x) >= 0.0; }   // one copy, not one per sine
+#endif
+MR_FN int mr_sin_ge0(double x) {
+    int ge = mr_sin_ge0_fast(x);                 // safe for any argument; repaired below (the cold block goes out of line)
+#ifndef MR_NO_SLOW   /* experiment only: measures what the out-of-range branches cost */
+    if (MR_UNLIKELY(!mr_sin_inrange_f(x))) ge = mr_sin_ge0_slow(x);
+#endif
+    return ge;
 }
 
 #ifndef MR_LIBM_HOST

@@ -149,6 +149,35 @@ int main(int argc, char** argv) {
         for (unsigned i = 0; i < sizeof sp / sizeof sp[0]; i++) bad += check_one("log", my_log, ref_log, sp[i], bad);
         report("log", "specials", (long)(sizeof sp / sizeof sp[0]), bad);
     }
+    // sign of the sine (mr_sin_ge0: what step(sin(u)) evaluates): equal to (sin(x) >= 0) of glibc's sine AND of the fast
+    // sine it replaces, everywhere -- multiples of pi/2 included, where the reduced argument nearly cancels.
+    {
+        long bad = 0, cnt = 0;
+        for (int pass = 0; pass < 3; pass++) {
+            const double hi_[] = {8.0, 4194304.0, 4.6e18};
+            for (long i = 0; i < n; i++) {
+                double x = pass < 2 ? hi_[pass] * uniform01() : from_bits(rng() % bits(hi_[pass]));
+                if (rng() & 1) x = -x;
+                const int a = mr_sin_ge0(x), b = libm_sin(x) >= 0.0;
+                const int c = mr_sin_inrange_f(x) ? (mr_sin_fast_f(x) >= 0.0) : b;
+                if (a != b || a != c) { if (bad < 4) printf("    sin_ge0(%a) = %d, glibc %d, fast %d\n", x, a, b, c); bad++; }
+                cnt++;
+            }
+        }
+        for (int k = -4000; k <= 4000; k++)
+            for (int d = -64; d <= 64; d++) {
+                const double m = k * 0x1.921fb54442d18p+0;
+                const double x = from_bits(bits(m < 0 ? -m : m) + (uint64_t)(int64_t)d) * (m < 0 ? -1.0 : 1.0);
+                if (k == 0 && d < 0) continue;
+                const int a = mr_sin_ge0(x), b = libm_sin(x) >= 0.0, c = mr_sin_fast_f(x) >= 0.0;
+                if (a != b || a != c) { if (bad < 4) printf("    sin_ge0(%a) = %d, glibc %d, fast %d\n", x, a, b, c); bad++; }
+                cnt++;
+            }
+        const double sp[] = {0.0, -0.0, inf, -inf, nan_, 0x1p-1074, -0x1p-1074, 0x1p-1022, 4194304.0, -4194304.0, 1e300};
+        for (unsigned i = 0; i < sizeof sp / sizeof sp[0]; i++, cnt++)
+            if (mr_sin_ge0(sp[i]) != (libm_sin(sp[i]) >= 0.0)) { printf("    sin_ge0(%a)\n", sp[i]); bad++; }
+        report("sgn", "sign of the sine, all ranges", cnt, bad);
+    }
     printf("total differing: %ld\n", total_bad);
     return total_bad ? 1 : 0;
 }
