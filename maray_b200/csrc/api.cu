@@ -371,6 +371,8 @@ int nvrtc_compile(JitBuild* jb, const std::atomic<bool>* cancel, bool cached_onl
     if (std::getenv("MARAY_JIT_NOSLOW")) options.push_back("-DMR_NO_SLOW=1");   // experiment only (wrong for huge/NaN arguments)
     if (jb->libm == MARAY_LIBM_CUDA) options.push_back("-DMR_LIBM_PLAIN=1");    // A/B: libdevice's sin/exp/log
     if (jb->libm == MARAY_LIBM_GLIBC) options.push_back("-DMR_LIBM_GLIBC=1");   // exact mode (device_libm_glibc.cuh)
+    if (const char* e = std::getenv("MARAY_LIBM_EXPLOG"))                       // A/B: round 1's polynomial exp and log
+        if (std::string(e) == "poly") options.push_back("-DMR_EXPLOG_POLY=1");
 
     jb->registers = 0;
     jb->compile_threads = 0;
@@ -705,7 +707,9 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
                 g.frame_cap = chunk * per_px;
             }
             unsigned long long fs = chunk;
+            static const bool poison = std::getenv("MARAY_JIT_FRAME_POISON") != nullptr;   // debugging: a value read before it is written is a NaN
             for (size_t done = 0; done < n; done += chunk) {
+                if (poison) CU_TRY(h, cudaMemsetAsync(g.d_frame, 0xff, g.frame_cap, stream));
                 MrParams q = p;
                 q.p0 = p0 + uint32_t(done);
                 q.n = uint32_t(std::min<size_t>(chunk, n - done));

@@ -146,8 +146,13 @@ struct Emitter {
             s += buf;
             switch (n.op) {
             case OP_STEP:
-                if (is_sign_only(n.a)) { s += "mr_sin_ge0("; operand(s, P.nodes[n.a].a); s += ")"; }   // step(sin(u)): the sign is enough
-                else { s += "("; operand(s, n.a); s += " >= 0.0)"; }                  // NaN -> false, -0.0 -> true
+                if (is_sign_only(n.a) && P.nodes[n.a].op == OP_SIN) {
+                    s += "mr_sin_ge0("; operand(s, P.nodes[n.a].a); s += ")";         // step(sin(u)): the sign is enough
+                } else if (is_sign_only(n.a)) {                                       // step(v + c)  ==  v >= -c  ==  -v <= c  (finite constant c)
+                    const Node& ad = P.nodes[n.a];
+                    const bool ca = P.nodes[ad.a].op == OP_CONST;
+                    s += "(-("; operand(s, ca ? ad.b : ad.a); s += ") <= "; operand(s, ca ? ad.a : ad.b); s += ")";   // -v <= c: c stays a bank operand
+                } else { s += "("; operand(s, n.a); s += " >= 0.0)"; }                // NaN -> false, -0.0 -> true
                 break;
             case OP_ADD: {                                                           // 1 + -(b)  ==  !b
                 const uint32_t neg = P.nodes[n.a].op == OP_NEG ? n.a : n.b;
@@ -223,6 +228,7 @@ std::vector<uint8_t> find_booleans(const Program& prog) {
     return kind;
 }
 
+// Values that are only ever asked for their sign, by one step, and are therefore never materialised.
 // step(sin(u)) where nothing else reads the sine -- Maray's `chess` is made of these (reference src/lib.rs:969-973) --
 // only needs the SIGN of the sine, which the argument reduction already decides: the polynomial, its table loads and
 // the quadrant selects are skipped (device_libm.cuh mr_sin_ge0; per sine 6 FP64 instructions instead of 16).  Exact:
@@ -239,7 +245,18 @@ std::vector<uint8_t> find_sign_only_sines(const Program& prog, const std::vector
     std::vector<uint8_t> mark(n, 0);
     for (size_t i = 0; i < n; i++) {
         const Node& nd = prog.nodes[i];
-        if (nd.op == OP_STEP && booleans[i] && prog.nodes[nd.a].op == OP_SIN && uses[nd.a] == 1) mark[nd.a] = 1;
+        if (nd.op != OP_STEP || !booleans[i] || uses[nd.a] != 1) continue;
+        const Node& arg = prog.nodes[nd.a];
+        if (arg.op == OP_SIN) mark[nd.a] = 1;
+        // step(v + c) with a finite constant c is the comparison v >= -c: the rounded sum is zero exactly when v == -c
+        // (sums of doubles never underflow to zero), otherwise it has the sign of the exact sum; v = +-inf and NaN give
+        // the same answer both ways because c is finite.  (Two variables would not do: inf - inf is NaN, inf >= inf is true.)
+        if (arg.op == OP_ADD && !booleans[nd.a]) {
+            const Node& x = prog.nodes[arg.a];
+            const Node& y = prog.nodes[arg.b];
+            const bool cx = x.op == OP_CONST && x.k - x.k == 0.0, cy = y.op == OP_CONST && y.k - y.k == 0.0;
+            if (cx != cy) mark[nd.a] = 1;
+        }
     }
     return mark;
 }

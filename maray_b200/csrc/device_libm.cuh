@@ -99,9 +99,7 @@ static __device__ __noinline__ double mr_slow_log(double x) { return log(x); }
 #define MR_LDG2(p, lo, hi) do { double2 v2_ = __ldg(reinterpret_cast<const double2*>(p)); (lo) = v2_.x; (hi) = v2_.y; } while (0)
 #endif
 
-#if defined(MR_LIBM_GLIBC) || defined(MR_LIBM_BOTH) || defined(MR_LIBM_HOST)
-#include "device_libm_glibc.cuh"   // exact mode: mr_*_inrange_g, mr_*_fast_g, mr_*_slow_g
-#endif
+#include "device_libm_glibc.cuh"   // glibc's routines: mr_*_inrange_g, mr_*_fast_g, mr_*_slow_g (exp and log ARE these)
 
 // Constants, read as constant-bank operands.
 MR_TABLE double MR_LK[] = {
@@ -123,6 +121,11 @@ MR_TABLE double MR_LK[] = {
     // leading coefficients of the sin / cos chains (selected by parity with FSEL)
     /* 26 */ -0x1.8dc40a95e2836p-41,     // sin S6
     /* 27 */ -0x1.9000fc0d9bc33p-37,     // cos C6
+    // reduction by pi (sign of the sine): entries 1..4 scaled by powers of two, so the same 160 bits
+    /* 28 */ 0x1.45f306dc9c883p-2,       // 1/pi
+    /* 29 */ 0x1.921fb54442d18p+1,       // pi high
+    /* 30 */ 0x1.1a62633145c06p-53,      // pi middle
+    /* 31 */ 0x1.c1cd129024e09p-106,     // pi low
 };
 
 // Remaining coefficients of the two chains, highest first, one 48-byte row per parity (16-byte
@@ -145,8 +148,17 @@ static __device__ __align__(16) const double MR_SINCOS[2][6] = {
 // The range tests look at the high word only (integer pipe, not the FP64 pipe); NaN and infinity
 // have a high word above every bound, so they always take the libdevice branch.
 MR_FN int mr_sin_inrange_f(double x) { return (unsigned int)(mr_hi32(x) & 0x7fffffff) < 0x41500000u; }   // |x| < 2^22
+#ifdef MR_EXPLOG_POLY   /* A/B only: round 1's polynomial exp and log */
 MR_FN int mr_exp_inrange_f(double x) { return (unsigned int)(mr_hi32(x) & 0x7fffffff) < 0x40862000u; }   // |x| < 708
 MR_FN int mr_log_inrange_f(double x) { return (unsigned int)(mr_hi32(x) - 0x00100000) < 0x7fe00000u; }   // positive normal
+#else
+// exp and log are glibc's algorithms in every mode (device_libm_glibc.cuh): fewer FP64 instructions than the
+// polynomial versions they replaced (12 and 15 against 17 and 30), dependency chains half as long -- which is what
+// bounds the batched helpers -- and the reference's bits.  exp: |x| < 512; tiny arguments need no special case here
+// (for |x| < 2^-54 the main path rounds 1 + x + x^2/2.. to exactly what glibc's early `1.0 + x` returns).
+MR_FN int mr_exp_inrange_f(double x) { return (unsigned int)((mr_hi32(x) >> 20) & 0x7ff) < 0x408u; }
+MR_FN int mr_log_inrange_f(double x) { return mr_log_inrange_g(x); }
+#endif
 
 // Straight-line fast paths: safe (no traps, no loops) for ANY argument, meaningful inside the range.
 MR_FN double mr_sin_fast_f(double x) {
@@ -176,6 +188,14 @@ MR_FN double mr_sin_fast_f(double x) {
     return mr_hilo((int)((unsigned int)mr_hi32(v) ^ (((unsigned int)qi & 2u) << 30)), mr_lo32(v));   // quadrants 2,3: negate
 }
 
+#ifndef MR_EXPLOG_POLY
+MR_FN double mr_exp_fast_f(double x) { return mr_exp_fast_g(x); }
+MR_FN double mr_log_fast_f(double x) { return mr_log_fast_g(x); }
+#undef MR_SLOW_EXP_F
+#undef MR_SLOW_LOG_F
+#define MR_SLOW_EXP_F(x) mr_exp_slow_g(x)
+#define MR_SLOW_LOG_F(x) mr_log_slow_g(x)
+#else
 // exp(x).  Fast range |x| < 708: n = rint(x*log2(e)), r = x - n*ln2 (two FMAs), degree-12 polynomial,
 // scaling by 2^n through the exponent field.
 MR_FN double mr_exp_fast_f(double x) {
@@ -236,6 +256,7 @@ MR_FN double mr_log_fast_f(double x) {
     const double lo = MR_FMA(ed, MR_LK[7], t3) + c;
     return h + lo;
 }
+#endif  // MR_EXPLOG_POLY
 
 
 // Which implementation the names below mean.  Default: the fast versions above.  MR_LIBM_GLIBC (MARAY_LIBM=glibc):
@@ -318,20 +339,20 @@ MR_FN double mr_log_eo(double x) {
 }
 
 // mr_sin(x) >= 0.0 without the sine: what `step(sin(u))` needs (Maray's `chess`, reference src/lib.rs:969-973).
-// The reduction x = q*pi/2 + r is the one of mr_sin_fast_f; in an even quadrant the value is +-(r + r*P) = +-r*(1 + P)
-// with |P| < 0.11, which has the sign of +-r (and is +-0 exactly when r is), in an odd quadrant it is +-(1 + s*C(s))
-// with the cosine in [0.7, 1].  The sign of the sine of a nonzero double is never in doubt at this accuracy, so the
-// same answer holds for glibc's sine (exact mode) as for the fast one.  Outside |x| < 2^22: the full routine.
+// x = k*pi + r with |r| <= pi/2 (the Cody-Waite reduction of mr_sin_fast_f, by pi instead of pi/2: the same 160 bits
+// of pi, first product exact): sin(x) = (-1)^k sin(r), and sin(r) has the sign of r and is +-0 exactly when r is.  The
+// reduced argument of a nonzero double is never closer to zero than ~2^-60 while r is good to ~2^-100 absolute here, so
+// the sign of r IS the sign of the true sine -- which every sine with a relative error bound returns, the fast one
+// above, libdevice's and glibc's (exact mode) alike.  Checked against both on the host (tools/glibc_libm_check.c, all
+// ranges and the neighbourhoods of 8 000 multiples of pi/2).  Outside |x| < 2^22: the full routine.
 MR_FN int mr_sin_ge0_fast(double x) {
-    const double t = MR_FMA(x, MR_LK[1], MR_LK[0]);
-    const double q = t - MR_LK[0];
-    double r = MR_FMA(q, -MR_LK[2], x);
-    r = MR_FMA(q, -MR_LK[3], r);
-    r = MR_FMA(q, -MR_LK[4], r);
-    const unsigned int qi = (unsigned int)mr_lo32(t);
-    // One compare decides, without a branch: of +-r in the even quadrants, of +-1.x (the cosine's sign) in the odd ones.
-    const unsigned int hi = (qi & 1u) ? 0x3ff00000u : (unsigned int)mr_hi32(r);
-    return mr_hilo((int)(hi ^ ((qi & 2u) << 30)), mr_lo32(r)) >= 0.0;
+    const double t = MR_FMA(x, MR_LK[28], MR_LK[0]);
+    const double k = t - MR_LK[0];
+    double r = MR_FMA(k, -MR_LK[29], x);
+    r = MR_FMA(k, -MR_LK[30], r);
+    r = MR_FMA(k, -MR_LK[31], r);
+    // r, or -r for odd k; -0 >= 0 holds, as step(-0.0) = 1 requires
+    return mr_hilo((int)((unsigned int)mr_hi32(r) ^ ((unsigned int)mr_lo32(t) << 31)), mr_lo32(r)) >= 0.0;
 }
 #ifdef MR_LIBM_HOST
 static int mr_sin_ge0_slow(double x) { return mr_sin_eo(x) >= 0.0; }
@@ -417,6 +438,7 @@ __device__ __forceinline__ void mr_sin_fast_w_f(const double* x, double* out) {
         out[i] = mr_hilo((int)((unsigned int)mr_hi32(v) ^ (((unsigned int)qi[i] & 2u) << 30)), mr_lo32(v));
     }
 }
+#ifdef MR_EXPLOG_POLY
 __device__ __forceinline__ void mr_exp_fast_w_f(const double* x, double* out) {
     double t[MR_W], n[MR_W], r[MR_W], p[MR_W];
     MR_EACH t[i] = MR_FMA(x[i], MR_LK[5], MR_LK[0]);
@@ -474,6 +496,56 @@ __device__ __forceinline__ void mr_log_fast_w_f(const double* x, double* out) {
     MR_EACH lo[i] = MR_FMA(ed[i], MR_LK[7], t3[i]) + c[i];
     MR_EACH out[i] = h[i] + lo[i];
 }
+#else
+// glibc's exp, MR_W evaluations step-major: same operations per lane as mr_exp_fast_g.
+__device__ __forceinline__ void mr_exp_fast_w_f(const double* x, double* out) {
+    double kd0[MR_W], kd[MR_W], r[MR_W], tail[MR_W], p23[MR_W], tr[MR_W], r2[MR_W], p45[MR_W], t1[MR_W], scale[MR_W];
+    MR_EACH kd0[i] = MR_FMA(x[i], MRG_EXP_K[0], MRG_EXP_K[1]);
+    MR_EACH kd[i] = kd0[i] - MRG_EXP_K[1];
+    MR_EACH r[i] = MR_FMA(kd[i], MRG_EXP_K[2], x[i]);
+    MR_EACH r[i] = MR_FMA(kd[i], MRG_EXP_K[3], r[i]);
+    MR_EACH {
+        const unsigned int ki = (unsigned int)mr_lo32(kd0[i]);
+        unsigned long long tb, sb;
+        MRG_LDG2U(MRG_EXP_TAB + 2 * (ki & 127u), tb, sb);
+        sb += (unsigned long long)ki << 45;
+        tail[i] = mr_hilo((int)(tb >> 32), (int)(unsigned int)tb);
+        scale[i] = mr_hilo((int)(sb >> 32), (int)(unsigned int)sb);
+    }
+    MR_EACH p23[i] = MR_FMA(r[i], MRG_EXP_K[5], MRG_EXP_K[4]);
+    MR_EACH tr[i] = r[i] + tail[i];
+    MR_EACH r2[i] = r[i] * r[i];
+    MR_EACH p45[i] = MR_FMA(r[i], MRG_EXP_K[7], MRG_EXP_K[6]);
+    MR_EACH t1[i] = MR_FMA(p23[i], r2[i], tr[i]);
+    MR_EACH r2[i] = r2[i] * r2[i];
+    MR_EACH t1[i] = MR_FMA(r2[i], p45[i], t1[i]);
+    MR_EACH out[i] = MR_FMA(scale[i], t1[i], scale[i]);
+}
+// glibc's log: the table path for all lanes step-major, then the lanes close to 1 (a different polynomial) again.
+__device__ __forceinline__ void mr_log_fast_w_f(const double* x, double* out) {
+    double z[MR_W], invc[MR_W], logc[MR_W], kd[MR_W], w[MR_W], r[MR_W], a12[MR_W], hi[MR_W], r2[MR_W], lo[MR_W], r3[MR_W], a34[MR_W];
+    MR_EACH {
+        const int hx = mr_hi32(x[i]);
+        const int th = hx - 0x3fe60000;
+        z[i] = mr_hilo(hx - (int)((unsigned int)th & 0xfff00000u), mr_lo32(x[i]));
+        MR_LDG2(MRG_LOG_TAB + 2 * ((th >> 13) & 127), invc[i], logc[i]);
+        kd[i] = (double)(th >> 20);
+    }
+    MR_EACH w[i] = MR_FMA(kd[i], MRG_LOG_K[0], logc[i]);
+    MR_EACH r[i] = MR_FMA(z[i], invc[i], -1.0);
+    MR_EACH a12[i] = MR_FMA(r[i], MRG_LOG_K[4], MRG_LOG_K[3]);
+    MR_EACH hi[i] = r[i] + w[i];
+    MR_EACH r2[i] = r[i] * r[i];
+    MR_EACH lo[i] = (w[i] - hi[i]) + r[i];
+    MR_EACH lo[i] = MR_FMA(kd[i], MRG_LOG_K[1], lo[i]);
+    MR_EACH r3[i] = r[i] * r2[i];
+    MR_EACH a34[i] = MR_FMA(r[i], MRG_LOG_K[6], MRG_LOG_K[5]);
+    MR_EACH lo[i] = MR_FMA(r2[i], MRG_LOG_K[2], lo[i]);
+    MR_EACH a34[i] = MR_FMA(a34[i], r2[i], a12[i]);
+    MR_EACH out[i] = MR_FMA(r3[i], a34[i], lo[i]) + hi[i];
+    MR_EACH if ((unsigned int)(mr_hi32(x[i]) - 0x3fee0000) < 0x30900u) out[i] = mr_log_fast_g(x[i]);
+}
+#endif  // MR_EXPLOG_POLY
 #ifdef MR_LIBM_GLIBC
 // The exact mode branches inside an evaluation (ranges of sin, the near-1 path of log), so it is not written step-major.
 #define MR_DEFINE_FAST_W(fn) __device__ __forceinline__ void mr_##fn##_fast_w(const double* x, double* out) { MR_EACH out[i] = mr_##fn##_fast_g(x[i]); }

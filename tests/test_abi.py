@@ -35,6 +35,9 @@ def test_no_torch_or_oracle_in_the_product():
         assert "from oracle" not in src and "import oracle" not in src
     out = os.popen(f"ldd {_lib.LIB_PATH}").read()
     assert "libtorch" not in out and "maray_oracle" not in out
+    # NVRTC is linked statically: which compiler builds the kernels must not depend on what else is in the process
+    # (PyTorch brings its own libnvrtc.so.12, an older one; DESIGN.md section 10 has the miscompile that exposed this).
+    assert "nvrtc" not in out and "libcudart" not in out
 
 
 def test_host_only_handle_compiles_but_cannot_render(chess_bytes):

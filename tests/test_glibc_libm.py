@@ -35,13 +35,15 @@ def _cpu_has_fma():
 @needs_glibc_239
 @pytest.mark.skipif(not _cpu_has_fma(), reason="glibc selects its FMA variants only on AVX2+FMA hosts")
 def test_exact_mode_returns_the_host_libms_bits(tmp_path):
-    exe = tmp_path / "glibc_libm_check"
-    subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fno-builtin-sin", "-fno-builtin-exp",
-                           "-fno-builtin-log", "-o", str(exe), os.path.join(ROOT, "tools", "glibc_libm_check.c"), "-lm"])
-    out = subprocess.run([str(exe), "2000000"], capture_output=True, text=True)
-    assert out.returncode == 0, out.stdout[-3000:]
-    assert "total differing: 0" in out.stdout
-    assert out.stdout.count(" 0 differ") >= 24          # every (function, range) line
+    """Exact mode: sin, exp, log and the sign of the sine.  Default mode (-DFAST_MODE): exp and log are the same routines
+    (only the sine differs), and the sign of the sine equals glibc's there too."""
+    for flags in ([], ["-DFAST_MODE"]):
+        exe = tmp_path / ("glibc_libm_check" + "_fast" * bool(flags))
+        subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fno-builtin-sin", "-fno-builtin-exp",
+                               "-fno-builtin-log", *flags, "-o", str(exe), os.path.join(ROOT, "tools", "glibc_libm_check.c"), "-lm"])
+        out = subprocess.run([str(exe), "2000000"], capture_output=True, text=True)
+        assert "total differing: 0" in out.stdout and out.returncode == 0, out.stdout[-3000:]
+        assert out.stdout.count(" 0 differ") >= 25          # every (function, range) line
 
 
 @needs_glibc_239

@@ -596,3 +596,22 @@ def test_fp64_peak_microbenchmark_is_sane():
         nofma, fma = r.fp64_peak(0)
     # nominal: 148 SMs x 64 lanes x <=1.965 GHz = 18.6e12 lane-ops/s
     assert 5e12 < nofma < 25e12 and 5e12 < fma < 25e12
+
+
+def test_chain_segmentations_render_the_same_frame(monkeypatch):
+    """Regression (round 2): the 7-kernel chain of the 20 000-value deep scene, built by the NVRTC 12.8 that PyTorch had
+    put into the process, rendered a different image (a miscompiled 2-wide sine helper); the generated text was right
+    (CPU-checked) and NVRTC 12.9 builds it correctly.  NVRTC is now linked statically; this pins the frames of three
+    segmentations to each other and to the oracle, with torch imported first as in bench.py."""
+    import torch  # noqa: F401  (what used to swap the compiler)
+    w = h = 512
+    scene = scenes.deep(w, h, n_values=20000, seed=1)
+    frames = []
+    for seg in ("6144", "3072", "1536"):
+        monkeypatch.setenv("MARAY_JIT_CHAIN_SEGMENT_VALUES", seg)
+        with _renderer(scene, "nvrtc") as r:
+            assert r.stats()["jit_segments"] == {"6144": 4, "3072": 7, "1536": 13}[seg]
+            frames.append(r.render(w, h))
+    assert np.array_equal(frames[0], frames[1]) and np.array_equal(frames[0], frames[2])
+    want_rgb, _ = OracleScene(scene).render_window(100, 132, 200, 208, want_f64=True)
+    assert np.abs(frames[1][200:208, 100:132].astype(int) - want_rgb.astype(int)).max() <= 1

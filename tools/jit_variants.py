@@ -59,6 +59,9 @@ for var in variants:
                 best = min(best, r.stats()["kernel_ms"][0])
             frame = r.render(w, h)
             digest = hashlib.sha256(frame.tobytes()).hexdigest()[:16]
+            if base_env.get("JIT_VARIANTS_DUMP"):      # debugging: keep the frames
+                import numpy as _np
+                _np.save(os.path.join(base_env["JIT_VARIANTS_DUMP"], "frame_%d.npy" % variants.index(var)), frame)
             if first is None:
                 first = digest
             rec.update({"kernel_ms": round(best, 3), "mpix_s": round(w * h / best / 1e3, 2),
