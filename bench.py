@@ -507,6 +507,22 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         if bound == "lsu":
             texel_bytes = int(stats["n_tex"]) * band_px
             roof["gather_store_GBps"] = (texel_bytes + 3 * band_px) / (kernel_ms_max * 1e-3) / 1e9
+        # what the generated kernel really executes (straight-line kernels only: one unit, no batched helper loops)
+        if args.backend != "interp" and stats["jit_units"] == 1 and stats["jit_segments"] <= 1:
+            try:
+                from maray_b200.roofline import executed_counts
+                ex = executed_counts(r.cubin(0))
+            except Exception:
+                ex = None
+            if ex:
+                roof["executed"] = {"fp64_instr_per_pixel": ex["fp64"], "all_instr_per_pixel": ex["all"],
+                                    "fp64_pipe_frac": band_px * ex["fp64"] / (kernel_ms_max * 1e-3) / peak_nofma if peak_nofma else None,
+                                    "source": "cuobjdump -sass of the kernel in use (maray_cuda_get_cubin)"}
+                if ex["fp64"] < ops_px:
+                    roof["note"] = (roof["note"] + " " if roof["note"] else "") + (
+                        f"`achieved` prices the reference's per-pixel evaluation ({ops_px} FP64 lane-operations); exact rewrites "
+                        f"(boolean logic, sign of a sine, step(v+c) as a comparison) leave {ex['fp64']} to execute, so the "
+                        "algorithmic fraction can exceed 1 -- `executed.fp64_pipe_frac` is the share of the FP64 pipe in use.")
         traffic = committed_dram_traffic(name, args.backend) if world == 1 else None
         roof["traffic"] = traffic["bytes"] if traffic else None
         roof["traffic_source"] = traffic["source"] if traffic else None

@@ -183,6 +183,9 @@ int maray_cuda_get_source(const maray_cuda_t* h, char* buf, size_t cap, size_t* 
  * above the segment size one kernel per segment, launched in order -- see stats.jit_segments).  Same calling
  * convention as maray_cuda_get_source; MARAY_E_INVALID when `index` is out of range. */
 int maray_cuda_get_module(const maray_cuda_t* h, uint32_t index, char* buf, size_t cap, size_t* len);
+/* The sm_100a cubin NVRTC produced for translation unit `index` (tooling: `cuobjdump -sass` of it is how the FP64-pipe
+ * instruction counts behind the roofline are read).  *len receives its size; at most cap bytes are copied. */
+int maray_cuda_get_cubin(const maray_cuda_t* h, uint32_t index, void* buf, size_t cap, size_t* len);
 /* Bytecode of the interpreter back end: 8-byte instructions, then the constant pool. */
 int maray_cuda_get_bytecode(const maray_cuda_t* h, uint64_t* code, size_t cap_instr, size_t* n_instr,
                             double* consts, size_t cap_consts, size_t* n_consts);

@@ -66,6 +66,7 @@ SYMBOLS = [
     ("maray_cuda_get_stats", ctypes.c_int, [_P, ctypes.POINTER(Stats)]),
     ("maray_cuda_get_source", ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     ("maray_cuda_get_module", ctypes.c_int, [_P, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    ("maray_cuda_get_cubin", ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     ("maray_cuda_get_bytecode", ctypes.c_int, [_P, _P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), _P,
                                                ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     ("maray_cuda_fp64_peak", ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),

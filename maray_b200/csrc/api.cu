@@ -1308,6 +1308,14 @@ int maray_cuda_get_module(const maray_cuda_t* h, uint32_t index, char* buf, size
     return MARAY_OK;
 }
 
+int maray_cuda_get_cubin(const maray_cuda_t* h, uint32_t index, void* buf, size_t cap, size_t* len) {
+    if (!h || index >= h->jit.cubins.size()) return MARAY_E_INVALID;
+    const std::vector<char>& c = h->jit.cubins[index];
+    if (len) *len = c.size();
+    if (buf && cap) std::memcpy(buf, c.data(), std::min(cap, c.size()));
+    return MARAY_OK;
+}
+
 int maray_cuda_get_bytecode(const maray_cuda_t* h, uint64_t* code, size_t cap_instr, size_t* n_instr, double* consts,
                             size_t cap_consts, size_t* n_consts) {
     if (!h) return MARAY_E_INVALID;

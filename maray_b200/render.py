@@ -178,6 +178,14 @@ class CudaRenderer:
             i += 1
         return out
 
+    def cubin(self, index: int = 0) -> bytes:
+        """The cubin of translation unit `index` of the NVRTC back end."""
+        n = ctypes.c_size_t()
+        self._check(self._L.maray_cuda_get_cubin(self._h, index, None, 0, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value)
+        self._check(self._L.maray_cuda_get_cubin(self._h, index, buf, n.value, ctypes.byref(n)))
+        return buf.raw
+
     def bytecode(self):
         ni, nk = ctypes.c_size_t(), ctypes.c_size_t()
         self._check(self._L.maray_cuda_get_bytecode(self._h, None, 0, ctypes.byref(ni), None, 0, ctypes.byref(nk)))
