@@ -381,3 +381,34 @@ def bits_equal(a, b):
     a = np.ascontiguousarray(a, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
     return (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))
+
+
+def sign_rewrite_scene(w):
+    """Steps whose operand is only asked for its sign: step(sin(u)) over zero, tiny, ordinary, huge (beyond the fast
+    range), infinite and NaN arguments; step(v + c) with v = +-inf, NaN, -0 and values equal to -c; and the same
+    operands with a second reader, which must NOT be rewritten."""
+    from maray_b200 import expr as E
+    X, Y = E.x(), E.y()
+    rat = lambda p, q: E.div(E.nat(p), E.nat(q))
+    inf = E.recip(E.sub(X, E.nat(3)))                       # +-inf at x = 3 ... finite elsewhere
+    nan = E.mul(inf, E.sub(X, E.nat(3)))                    # NaN at x = 3 (inf * 0)
+    u_small = E.mul(E.sub(X, E.nat(8)), rat(1, 7))          # crosses zero at x = 8 (+0 there)
+    u_neg0 = E.mul(E.neg(E.sub(X, E.nat(8))), E.nat(0))     # -0 / +0
+    u_big = E.mul(E.mul(X, X), E.mul(X, E.nat(4000000)))    # up to ~1e11: out of the fast range
+    s1 = E.step(E.sin(E.mul(u_small, E.add(Y, E.nat(1)))))
+    s2 = E.step(E.sin(u_neg0))
+    s3 = E.step(E.sin(u_big))
+    s4 = E.step(E.sin(E.add(inf, nan)))
+    sv = E.sin(E.mul(X, rat(5, 3)))
+    s5 = E.add(E.step(sv), sv)                              # the sine has a second reader
+    c1 = E.step(E.add(E.mul(X, rat(1, 4)), E.neg(E.nat(2))))            # zero sum at x = 8
+    c2 = E.step(E.add(E.nat(5), inf))
+    c3 = E.step(E.add(nan, rat(1, 3)))
+    c4 = E.step(E.add(u_neg0, E.nat(0)))
+    sm = E.add(E.mul(X, rat(1, 8)), E.neg(E.nat(1)))
+    c5 = E.mul(E.step(sm), sm)                              # the sum has a second reader
+    r = E.add(E.add(E.add(s1, E.mul(s2, E.nat(2))), E.add(E.mul(s3, E.nat(4)), E.mul(s4, E.nat(8)))), E.mul(s5, E.nat(16)))
+    g = E.add(E.add(E.add(c1, E.mul(c2, E.nat(2))), E.add(E.mul(c3, E.nat(4)), E.mul(c4, E.nat(8)))), E.mul(c5, E.nat(16)))
+    return E.to_bytes([w, 4], [r, g, E.add(r, g)])
+
+

@@ -17,7 +17,7 @@ from maray_b200 import CudaRenderer, scenes
 from maray_b200 import expr as E
 
 from conftest import ROOT
-from helpers import bits_equal
+from helpers import bits_equal, sign_rewrite_scene
 
 GLIBC = platform.libc_ver()
 needs_glibc_239 = pytest.mark.skipif(GLIBC[0] != "glibc" or GLIBC[1] != "2.39" or platform.machine() != "x86_64",
@@ -111,6 +111,27 @@ def test_deep_scene_is_bit_exact_in_exact_mode(backend):
             want_rgb, want = oracle.render_window(x0, x0 + 32, y0, y0 + 16, want_f64=True)
             assert bits_equal(planes, want).all()
             assert np.array_equal(rgb, want_rgb)
+
+
+@pytest.mark.gpu
+@needs_glibc_239
+@pytest.mark.parametrize("backend", ["nvrtc", "interp"])
+def test_sign_only_rewrites_on_device(backend):
+    """step(sin(u)) as the sign of the sine and step(v + c) as a comparison (codegen.cpp find_sign_only_sines) over zero,
+    -0, tiny, huge, infinite and NaN operands: exact mode reproduces the oracle's f64 values bit for bit, the default mode
+    its bytes; the interpreter (which evaluates the full sine) agrees with the generated kernels."""
+    from oracle.oracle import OracleScene
+    w, h = 32, 4
+    scene = sign_rewrite_scene(w)
+    want_rgb, want = OracleScene(scene).render_window(0, w, 0, h, want_f64=True)
+    for libm in ("glibc", "fast"):
+        with CudaRenderer(gpus=1) as r:
+            r.load(scene)
+            r.compile(backend, libm=libm)
+            planes, rgb = r.render_window_f64(w, h, 0, w, 0, h)
+        assert np.array_equal(rgb, want_rgb), libm
+        if libm == "glibc":
+            assert bits_equal(planes, want).all()
 
 
 @needs_glibc_239

@@ -11,7 +11,7 @@ from maray_b200 import CudaRenderer, scenes
 from maray_b200 import expr as E
 from oracle.oracle import OracleScene
 
-from helpers import as_u8, bits_equal, bytecode_run, host_chain_run, host_jit_run
+from helpers import as_u8, bits_equal, bytecode_run, host_chain_run, host_jit_run, sign_rewrite_scene
 
 
 def _oracle_window(scene, textures, x0, x1, y0, y1):
@@ -237,6 +237,25 @@ def test_nan_inf_and_zero_sign_semantics():
         E.mul(E.step(E.mul(xm, negzero)), E.add(E.mul(inf, xm), E.nat(300))),   # step(-0)=1, inf*0=NaN
     ]
     _check_scene(E.to_bytes([9, 2], color), 9, [0, 1])
+
+
+def test_sign_only_rewrites_keep_every_value(monkeypatch):
+    """codegen.cpp find_sign_only_sines: step(sin(u)) -> mr_sin_ge0(u), step(v + c) -> -v <= c.  The generated text
+    (host-compiled) must reproduce the oracle bit for bit with the rewrites and without."""
+    scene = sign_rewrite_scene(32)
+    with CudaRenderer(gpus=0) as r:
+        r.load(scene)
+        r.compile("nvrtc")
+        src = r.source()
+    assert src.count("mr_sin_ge0(") >= 4 + 1 and src.count(") <= ") >= 4      # (+1: the definition in the prelude)
+    assert "mr_sin(" in src[src.index('extern "C" __global__'):]               # the sine with two readers stays a sine
+    _check_scene(scene, 32, [0, 1, 3])
+    monkeypatch.setenv("MARAY_JIT_SIGN_OF_SINE", "0")
+    with CudaRenderer(gpus=0) as r:
+        r.load(scene)
+        r.compile("nvrtc")
+        assert "mr_sin_ge0(" not in r.source()[r.source().index('extern "C" __global__'):]
+    _check_scene(scene, 32, [0, 1, 3])
 
 
 def test_hoisting_option_is_value_preserving(monkeypatch, chess_bytes):
