@@ -616,3 +616,27 @@ def test_chain_segmentations_render_the_same_frame(monkeypatch):
     assert np.array_equal(frames[0], frames[1]) and np.array_equal(frames[0], frames[2])
     want_rgb, _ = OracleScene(scene).render_window(100, 132, 200, 208, want_f64=True)
     assert np.abs(frames[1][200:208, 100:132].astype(int) - want_rgb.astype(int)).max() <= 1
+
+
+def test_code_generation_knobs_render_the_same_frame(monkeypatch):
+    """The forms the code generator can take for a transcendental-heavy program (helper width, scratch or register
+    arguments, literal or banked constants, libm flavour for exp/log, segment functions instead of a chain) must all
+    render the bytes of the default form: the class of fault the NVRTC 12.8 miscompile belonged to."""
+    w, h = 384, 256
+    scene = scenes.deep(w, h, n_values=12000, seed=2)
+    with _renderer(scene, "nvrtc") as r:
+        want = r.render(w, h)
+    variants = [{"MARAY_JIT_BATCH_WIDTH": "4"}, {"MARAY_JIT_SCRATCH": "0"}, {"MARAY_JIT_CONST_BANK": "0"},
+                {"MARAY_JIT_CHAIN": "0", "MARAY_JIT_SEGMENT_VALUES": "4096"}, {"MARAY_JIT_CHAIN_SEGMENT_VALUES": "2000", "MARAY_JIT_SEGMENT_VALUES": "4096"},
+                {"MARAY_LIBM_EXPLOG": "poly"}, {"MARAY_JIT_BOOLEAN": "0"}, {"MARAY_JIT_LINEINFO": "0"}]
+    for env in variants:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with _renderer(scene, "nvrtc") as r:
+            got = r.render(w, h)
+        for k in env:
+            monkeypatch.delenv(k)
+        if "MARAY_LIBM_EXPLOG" in env:       # other (1-ULP) exp/log: the bytes may move by one grey level at most
+            assert np.abs(got.astype(int) - want.astype(int)).max() <= 1, env
+        else:
+            assert np.array_equal(got, want), env
