@@ -120,8 +120,8 @@ int maray_cuda_scene_size(const maray_cuda_t* h, uint32_t* w, uint32_t* hgt);
 
 /* Which sin/exp/ln the device evaluates `Expr::Sin/Exp/Ln` with (reference src/lib.rs:648-650 calls the platform
  * libm; src/wasm.rs:11-13 imports the same functions).  Takes effect at the next maray_cuda_compile.
- *   MARAY_LIBM_FAST   the default: 15 / 17 / 30 FP64 instructions, <= 1.5 / 0.86 / 0.58 ULP -- equal to glibc's result
- *                     in 84-99 % of arguments, one ULP away in the rest;
+ *   MARAY_LIBM_FAST   the default: exp and ln are glibc's algorithms (bit-exact); sin is a fast version, 18 FP64
+ *                     instructions, <= 1.8 ULP, equal to glibc's result in ~80 % of arguments and one ULP away otherwise;
  *   MARAY_LIBM_GLIBC  exact mode: glibc 2.39's own algorithms (x86-64 FMA variants) operation for operation, so every
  *                     value has the bits the reference computes on such a host (|x| >= 105414350 in sin excepted);
  *   MARAY_LIBM_CUDA   libdevice's sin/exp/log (A/B).

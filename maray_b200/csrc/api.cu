@@ -371,6 +371,8 @@ int nvrtc_compile(JitBuild* jb, const std::atomic<bool>* cancel, bool cached_onl
     if (std::getenv("MARAY_JIT_NOSLOW")) options.push_back("-DMR_NO_SLOW=1");   // experiment only (wrong for huge/NaN arguments)
     if (jb->libm == MARAY_LIBM_CUDA) options.push_back("-DMR_LIBM_PLAIN=1");    // A/B: libdevice's sin/exp/log
     if (jb->libm == MARAY_LIBM_GLIBC) options.push_back("-DMR_LIBM_GLIBC=1");   // exact mode (device_libm_glibc.cuh)
+    if (const char* e = std::getenv("MARAY_LIBM_SIN"))                          // A/B: round 1's quadrant-parity sine
+        if (std::string(e) == "parity") options.push_back("-DMR_SIN_PARITY=1");
     if (const char* e = std::getenv("MARAY_LIBM_EXPLOG"))                       // A/B: round 1's polynomial exp and log
         if (std::string(e) == "poly") options.push_back("-DMR_EXPLOG_POLY=1");
 

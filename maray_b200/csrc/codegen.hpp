@@ -52,8 +52,10 @@ struct CodegenOptions {
     // shared memory to leaf helpers (device_libm.cuh, "scratch-batched form") instead of through the
     // call ABI's registers.  false = the register-argument x4/x2 helpers.
     bool scratch_batches = true;
-    // Independent evaluations per iteration of the batch helpers' loop (2 or 4).
-    uint32_t batch_width = 2;
+    // Independent evaluations per iteration of the batch helpers' loop (2 or 4).  4 since the sine lost its table
+    // loads and selects (measured, deep scene at 20 000 values: 13.4 ms against 13.8 with 2; with round 1's sine 4 did
+    // not pay: the helper has the ~38 registers its caller leaves).
+    uint32_t batch_width = 4;
     // In a segmented single-unit program every segment function gets its own copy of the batch helpers.
     bool private_batch_helpers = true;
     // Evaluate values that are exactly 0.0 or 1.0 at every pixel (step, products/min/max of such

@@ -1,16 +1,14 @@
 // sin / exp / log for the render path (Expr::Sin/Exp/Ln, reference src/lib.rs:648-650).
 //
-// Why not CUDA's libdevice versions: they are accurate, but each call costs ~25 instructions that
-// are not FP64 work (constants rebuilt with two 32-bit moves each, special-case branches, address
-// arithmetic) -- measured on the chess scene, that is a quarter of all issue slots.  These versions
-// do the same mathematics with every constant read as a c[bank][offset] operand and one rarely
-// taken branch to the libdevice routine for arguments outside the fast range (huge, NaN, infinity,
-// subnormal).  Accuracy measured on the host rendition (tools/libm_check.c, 2e6 samples per range,
-// against 80-bit libm): sin <= 1.5 ULP (the reduced argument is a single double, as in libdevice),
-// exp <= 0.86 ULP, log <= 0.58 ULP -- inside CUDA's own documented bounds (2 / 1 / 1 ULP).  Coefficients: tools/gen_libm_coeffs.py.
+// exp and log: glibc's algorithms, restated in device_libm_glibc.cuh -- the reference's bits, and cheaper than the
+// polynomial versions they replaced.  sin: a fast version here (reduction by pi, one odd polynomial; <= 1.8 ULP measured
+// on the host rendition against 80-bit libm, tools/libm_check.c, 2e6 samples per range), or glibc's own in exact mode
+// (MR_LIBM_GLIBC).  Why not CUDA's libdevice: its routines are accurate, but each call costs ~25 instructions that are not
+// FP64 work (constants rebuilt with two 32-bit moves each, special-case branches, address arithmetic); here every constant
+// is a constant-bank operand and arguments outside the fast range take one rarely taken branch to an out-of-line routine.
 //
-// The same text compiles for the host when MR_LIBM_HOST is defined (fma() for __fma_rn), which is
-// how the accuracy numbers above are produced without a GPU.
+// The same text compiles for the host when MR_LIBM_HOST is defined (fma() for __fma_rn), which is how the accuracy numbers
+// and the bit-for-bit comparison with glibc (tools/glibc_libm_check.c) are produced without a GPU.
 #ifndef MARAY_DEVICE_LIBM_CUH
 #define MARAY_DEVICE_LIBM_CUH
 
@@ -126,6 +124,10 @@ MR_TABLE double MR_LK[] = {
     /* 29 */ 0x1.921fb54442d18p+1,       // pi high
     /* 30 */ 0x1.1a62633145c06p-53,      // pi middle
     /* 31 */ 0x1.c1cd129024e09p-106,     // pi low
+    // sin(r) = r + r*s*S(s), s = r*r, |r| <= pi/2: S of degree 8, lowest first (relative error 2^-58.7; tools/gen_libm_coeffs.py)
+    /* 32 */ -0x1.5555555555555p-3, 0x1.11111111110a9p-7, -0x1.a01a01a010c5cp-13, 0x1.71de3a4f8ab99p-19,
+    /* 36 */ -0x1.ae64528659a2dp-26, 0x1.6122db98108c0p-33, -0x1.add52c09d1f58p-41, 0x1.6dc19ddd0cdfbp-49,
+    /* 40 */ 0x1.4b52654981457p-56,
 };
 
 // Remaining coefficients of the two chains, highest first, one 48-byte row per parity (16-byte
@@ -161,6 +163,35 @@ MR_FN int mr_log_inrange_f(double x) { return mr_log_inrange_g(x); }
 #endif
 
 // Straight-line fast paths: safe (no traps, no loops) for ANY argument, meaningful inside the range.
+#ifndef MR_SIN_PARITY
+// sin(x), fast version: x = k*pi + r, |r| <= pi/2 (three FMAs over 160 bits of pi, the first product exact),
+// sin(x) = (-1)^k (r + r*s*S(s)).  One polynomial for every argument -- no parity-dependent coefficient rows, hence no
+// table loads and no selects --, evaluated by Estrin's scheme: eight FMAs in four dependent steps.  More FP64 instructions
+// than the quadrant version it replaced (20 against 15) but a chain of 12 instead of 16 and a third fewer instructions
+// overall, which is what counts in the batched helpers (latency-bound: DESIGN.md 3.1).  sin(-0) = -0: S*s is made +0 by
+// an explicit +0.0 addend, so the last FMA adds (-0) to (-0).
+MR_FN double mr_sin_fast_f(double x) {
+    const double t = MR_FMA(x, MR_LK[28], MR_LK[0]);
+    const double k = t - MR_LK[0];
+    double r = MR_FMA(k, -MR_LK[29], x);
+    r = MR_FMA(k, -MR_LK[30], r);
+    r = MR_FMA(k, -MR_LK[31], r);
+    const double s = r * r;
+    // the six high coefficients by Estrin's scheme (three independent FMAs, then two steps), the three low ones by
+    // Horner's: the low end decides the rounding error, the high end the length of the chain
+    const double p34 = MR_FMA(MR_LK[36], s, MR_LK[35]);
+    const double p56 = MR_FMA(MR_LK[38], s, MR_LK[37]);
+    const double p78 = MR_FMA(MR_LK[40], s, MR_LK[39]);
+    const double s2 = s * s;
+    double S = MR_FMA(p56, s2, p34);
+    S = MR_FMA(p78, s2 * s2, S);
+    S = MR_FMA(S, s, MR_LK[34]);
+    S = MR_FMA(S, s, MR_LK[33]);
+    S = MR_FMA(S, s, MR_LK[32]);
+    const double v = MR_FMA(MR_FMA(S, s, 0.0), r, r);
+    return mr_hilo((int)((unsigned int)mr_hi32(v) ^ ((unsigned int)mr_lo32(t) << 31)), mr_lo32(v));   // odd k: negate
+}
+#else   /* A/B only: round 1's sine (reduction by pi/2, one 7-step chain chosen by the quadrant's parity) */
 MR_FN double mr_sin_fast_f(double x) {
     const double t = MR_FMA(x, MR_LK[1], MR_LK[0]);
     const double q = t - MR_LK[0];
@@ -187,6 +218,8 @@ MR_FN double mr_sin_fast_f(double x) {
     const double v = odd ? p : sn;
     return mr_hilo((int)((unsigned int)mr_hi32(v) ^ (((unsigned int)qi & 2u) << 30)), mr_lo32(v));   // quadrants 2,3: negate
 }
+
+#endif  // MR_SIN_PARITY
 
 #ifndef MR_EXPLOG_POLY
 MR_FN double mr_exp_fast_f(double x) { return mr_exp_fast_g(x); }
@@ -408,6 +441,30 @@ extern __shared__ double mr_dyn_f64[];
 // (Left to itself the compiler emits one whole chain after the other -- measured: 47 % of the helpers'
 // cycles were fixed-latency waits on the previous DFMA with 4 warps per scheduler.)  Same operations in
 // the same order per lane as mr_sin_fast / mr_exp_fast / mr_log_fast: bit-identical results.
+#ifndef MR_SIN_PARITY
+__device__ __forceinline__ void mr_sin_fast_w_f(const double* x, double* out) {
+    double t[MR_W], k[MR_W], r[MR_W], s[MR_W], p34[MR_W], p56[MR_W], p78[MR_W], s2[MR_W], S[MR_W];
+    MR_EACH t[i] = MR_FMA(x[i], MR_LK[28], MR_LK[0]);
+    MR_EACH k[i] = t[i] - MR_LK[0];
+    MR_EACH r[i] = MR_FMA(k[i], -MR_LK[29], x[i]);
+    MR_EACH r[i] = MR_FMA(k[i], -MR_LK[30], r[i]);
+    MR_EACH r[i] = MR_FMA(k[i], -MR_LK[31], r[i]);
+    MR_EACH s[i] = r[i] * r[i];
+    MR_EACH p34[i] = MR_FMA(MR_LK[36], s[i], MR_LK[35]);
+    MR_EACH p56[i] = MR_FMA(MR_LK[38], s[i], MR_LK[37]);
+    MR_EACH p78[i] = MR_FMA(MR_LK[40], s[i], MR_LK[39]);
+    MR_EACH s2[i] = s[i] * s[i];
+    MR_EACH S[i] = MR_FMA(p56[i], s2[i], p34[i]);
+    MR_EACH S[i] = MR_FMA(p78[i], s2[i] * s2[i], S[i]);
+    MR_EACH S[i] = MR_FMA(S[i], s[i], MR_LK[34]);
+    MR_EACH S[i] = MR_FMA(S[i], s[i], MR_LK[33]);
+    MR_EACH S[i] = MR_FMA(S[i], s[i], MR_LK[32]);
+    MR_EACH {
+        const double v = MR_FMA(MR_FMA(S[i], s[i], 0.0), r[i], r[i]);
+        out[i] = mr_hilo((int)((unsigned int)mr_hi32(v) ^ ((unsigned int)mr_lo32(t[i]) << 31)), mr_lo32(v));
+    }
+}
+#else
 __device__ __forceinline__ void mr_sin_fast_w_f(const double* x, double* out) {
     double t[MR_W], q[MR_W], r[MR_W], s[MR_W], p[MR_W], k[MR_W][6], sn[MR_W];
     int qi[MR_W], odd[MR_W];
@@ -438,6 +495,7 @@ __device__ __forceinline__ void mr_sin_fast_w_f(const double* x, double* out) {
         out[i] = mr_hilo((int)((unsigned int)mr_hi32(v) ^ (((unsigned int)qi[i] & 2u) << 30)), mr_lo32(v));
     }
 }
+#endif  // MR_SIN_PARITY
 #ifdef MR_EXPLOG_POLY
 __device__ __forceinline__ void mr_exp_fast_w_f(const double* x, double* out) {
     double t[MR_W], n[MR_W], r[MR_W], p[MR_W];

@@ -11,7 +11,7 @@ it (profiles/sass_ops_r01.txt; regenerate with profiles/dump_op_sass.sh):
     min, max   2   (DSETP.GT|LT + DSETP.NAN, 2-4 FSEL on the integer pipe)
     recip      5   (MUFU.RCP64H on the XU pipe + 5 DFMA Newton steps)
     sqrt       8   (MUFU.RSQ64H + 3 DMUL + 5 DFMA)
-    sin       15   (1 DSETP + 2 DMUL + 11 DFMA + 1 DADD; F2I/I2F and 3 LDG.128 of coefficients not counted)
+    sin       18   (13 DFMA + 4 DMUL + 1 DADD: reduction by pi, nine coefficients, Estrin/Horner hybrid; round 1's quadrant version was 15)
     exp       12   (8 DFMA + 2 DADD + 2 DMUL: glibc's exp, the table load not counted; round 1's polynomial was 15)
     ln        14   (9 DFMA + 3 DADD + 2 DMUL: glibc's log, table path; I2F and the table load not counted; round 1: 28)
     tex        2   (the two `< 0.0` compares; conversions and the byte load are not FP64-pipe work)
@@ -30,7 +30,7 @@ from __future__ import annotations
 
 OP_WEIGHTS = {
     "n_add": 1, "n_mul": 1, "n_neg": 0, "n_abs": 0, "n_step": 1, "n_min": 2, "n_max": 2,
-    "n_recip": 5, "n_sqrt": 8, "n_sin": 15, "n_exp": 12, "n_ln": 14, "n_tex": 2,
+    "n_recip": 5, "n_sqrt": 8, "n_sin": 18, "n_exp": 12, "n_ln": 14, "n_tex": 2,
 }
 
 

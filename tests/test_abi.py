@@ -50,7 +50,7 @@ def test_host_only_handle_compiles_but_cannot_render(chess_bytes):
         assert st["n_min"] == 768 and st["n_max"] == 256 and st["n_recip"] == 0 and st["n_sqrt"] == 0
         assert st["dag_nodes"] == st["n_const"] + st["n_x_only"] + st["n_y_only"] + st["n_xy"] + 0
         assert st["interp_instructions"] > st["n_xy"] and 2 < st["interp_slots"] < 400
-        assert fp64_ops_per_pixel(st) == st["n_add"] + st["n_mul"] + st["n_step"] + 2 * 1024 + 15 * 256
+        assert fp64_ops_per_pixel(st) == st["n_add"] + st["n_mul"] + st["n_step"] + 2 * 1024 + 18 * 256
         with pytest.raises(MarayCudaError) as ei:
             r.render(64, 64)
         assert ei.value.code == _lib.E_CUDA and "no CPU fallback" in ei.value.message
