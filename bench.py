@@ -7,7 +7,7 @@
 
 A "step" renders one whole frame of the workload.  One process per GPU: rank r renders its row band
 on its own GPU through the C ABI (maray_cuda_render_band); at N > 1 the band kernels store straight into
-rank 0's frame over NVLink (CUDA IPC mapping) and a one-element all-reduce signals completion -- the
+rank 0's frame over NVLink (CUDA IPC mapping) and a one-element reduce to rank 0 signals completion -- the
 path's only exchange.  Rank 0 prints ONE JSON line.
 
   value     whole-frame Mpixel/s of the headline workload (chess_4k), frame left in HBM on rank 0
@@ -316,7 +316,7 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
 
     value    whole-frame Mpixel/s, frame left in rank 0's HBM.  N = 1: the band IS the frame.  N > 1: every rank's
              band kernel stores straight into rank 0's frame over NVLink (CUDA IPC mapping); the step ends with a
-             one-element all-reduce, the signal that every band has landed -- the path's only exchange.
+             one-element reduce to rank 0, the signal that every band has landed -- the path's only exchange.
     e2e      N = 1: the C ABI's maray_cuda_render into a PAGEABLE host image (what a Rust Vec<u8>/RgbImage is).
              N > 1: every rank renders its band locally and copies it over its own PCIe link into one pinned host
              frame shared by the ranks (POSIX shared memory), then the same completion signal.
@@ -375,7 +375,7 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
     def step_device():
         r.render_band(w, h, y0, y1, frame_ptr + y0 * w * 3, stream.cuda_stream)
         if world > 1:
-            dist.all_reduce(flag)                # every band has landed in rank 0's frame
+            dist.reduce(flag, dst=0)             # rank 0 learns that every band has landed in its frame
 
     peak_nofma, peak_fma = r.fp64_peak(0)        # roofline denominator of this GPU, before the timed region
 
@@ -396,7 +396,7 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         r.render_band(w, h, y0, y1, frame_ptr + y0 * w * 3, stream.cuda_stream)
         kev[i][1].record(stream)
         if world > 1:
-            dist.all_reduce(flag)
+            dist.reduce(flag, dst=0)
         ev[i][1].record(stream)
         flush.zero_()            # L2 flush between steps, outside the event pairs
         if world > 1:
@@ -446,11 +446,23 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         host_band = shm.band_view(y0, y1)                                      # this rank's rows of the shared host frame
         pinned = bool(host_band.is_pinned()) if nbytes else True
 
+        # the band in two halves: the first half travels to the host while the second renders (two halves of a
+        # 13.7-round band are 7 rounds each -- no more rounds than the whole band; finer cuts would add rounds)
+        copy_stream = torch.cuda.Stream(device=dev)
+        ym = y0 + (y1 - y0 + 1) // 2
+        halves = [(ya, yb) for ya, yb in ((y0, ym), (ym, y1)) if yb > ya]
+        half_done = [torch.cuda.Event() for _ in halves]
+
         def step_e2e():
-            r.render_band(w, h, y0, y1, band_dev.data_ptr(), stream.cuda_stream)
-            if nbytes:
-                host_band.copy_(band_dev[:nbytes], non_blocking=True)           # device -> host over this GPU's PCIe link
-            dist.all_reduce(flag)
+            for (ya, yb), evh in zip(halves, half_done):
+                lo, hi = (ya - y0) * w * 3, (yb - y0) * w * 3
+                r.render_band(w, h, ya, yb, band_dev.data_ptr() + lo, stream.cuda_stream)
+                evh.record(stream)
+                copy_stream.wait_event(evh)
+                with torch.cuda.stream(copy_stream):
+                    host_band[lo:hi].copy_(band_dev[lo:hi], non_blocking=True)   # device -> host over this GPU's PCIe link
+            stream.wait_stream(copy_stream)
+            dist.reduce(flag, dst=0)             # rank 0 learns that every band is in the host frame
             torch.cuda.synchronize()
 
         for _ in range(e2e_warm):
@@ -465,7 +477,7 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         e2e_value = w * h / float(te[0]) / 1e6
         e2e_pinned = None
         e2e_ok = bool(rank != 0 or np.array_equal(shm.image, frame_host))
-        e2e_how = ("every rank copies its band over its own PCIe link into one pinned host frame shared by the ranks "
+        e2e_how = ("every rank copies its band, in two halves that overlap the rendering, over its own PCIe link into one pinned host frame shared by the ranks "
                    f"(POSIX shared memory, cudaHostRegister rc {reg_rc}, pinned {pinned}); "
                    f"frame equals the device-path frame: {e2e_ok}")
         barrier()
@@ -530,7 +542,7 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
             "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
             "config": {"workload": name, "width": w, "height": h, "backend": args.backend,
                        "parallelism": (f"row bands x{world}: band kernels store into rank 0's frame over NVLink (CUDA IPC), "
-                                       "one 4-byte all-reduce per step signals completion") if world > 1 else "1 GPU",
+                                       "one 4-byte reduce to rank 0 per step signals completion") if world > 1 else "1 GPU",
                        "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
                        "dag_values": stats["dag_nodes"], "fp64_ops_per_pixel": ops_px},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": w * h * 3,
