@@ -66,4 +66,6 @@ def executed_counts(cubin: bytes, kernel: str = "maray_jit"):
             continue
         total += 1
         fp64 += op in ("DFMA", "DMUL", "DADD", "DSETP")
+        if op == "EXIT" and total > 64:      # end of the kernel's own path: out-of-line device functions (libdevice
+            break                            # fall-backs, the checked copy of a speculated program) follow it
     return {"fp64": fp64, "all": total} if total else None
