@@ -514,8 +514,8 @@ int jit_build(const Program& prog, JitBuild* jb, bool cached_only, const std::at
     if (const char* e = std::getenv("MARAY_JIT_SCRATCH")) copt.scratch_batches = std::strtoul(e, nullptr, 10) != 0;
     if (const char* e = std::getenv("MARAY_JIT_PRIVATE_HELPERS")) copt.private_batch_helpers = std::strtoul(e, nullptr, 10) != 0;
     if (const char* e = std::getenv("MARAY_JIT_BATCH_WIDTH")) copt.batch_width = uint32_t(std::strtoul(e, nullptr, 10));
-    if (const char* e = std::getenv("MARAY_JIT_BLOCK")) copt.block = uint32_t(std::strtoul(e, nullptr, 10));
-    if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10));
+    if (const char* e = std::getenv("MARAY_JIT_BLOCK")) { copt.block = uint32_t(std::strtoul(e, nullptr, 10)); copt.auto_shape = false; }
+    if (const char* e = std::getenv("MARAY_JIT_MIN_BLOCKS")) { copt.min_blocks_per_sm = uint32_t(std::strtoul(e, nullptr, 10)); copt.auto_shape = false; }
     jb->maxreg = 0;
     if (const char* e = std::getenv("MARAY_JIT_MAXREG")) jb->maxreg = unsigned(std::strtoul(e, nullptr, 10));
     // Programs above the segment size compile as a CHAIN of kernels, one translation unit each (codegen.hpp):
@@ -581,9 +581,26 @@ int jit_install(maray_cuda* h, JitBuild&& jb) {
             CU_TRY(h, cudaLibraryGetKernel(&kern, lib, kJitKernelName));
             g.jit_kernels.push_back(kern);
             cudaFuncAttributes fa;
-            if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(kern)) == cudaSuccess)
+            if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(kern)) == cudaSuccess) {
                 h->stats.jit_registers = std::max(h->stats.jit_registers, uint32_t(fa.numRegs));
-            else cudaGetLastError();
+                // Shared-memory carve-out: no more than the resident blocks use, the rest of the 256 KB is L1.  Left to
+                // itself the driver sizes it for the shared-memory occupancy limit (132 KB for the 33 KB scratch kernels,
+                // whose registers allow two blocks), and the spilled values of a large program then miss in a 121 KB L1.
+                int pct = -1;
+                if (const char* e = std::getenv("MARAY_JIT_CARVEOUT")) pct = int(std::strtol(e, nullptr, 10));   // percent; -1 = computed, -2 = driver's choice
+                if (pct == -1) {
+                    unsigned regs = std::max(1, fa.numRegs), blk = std::max(1u, h->jit_block);
+                    unsigned per_thread = (regs + 7) / 8 * 8;
+                    unsigned blocks = std::max(1u, std::min(std::min(65536u / (per_thread * blk), 2048u / blk), 32u));
+                    size_t need = size_t(blocks) * (h->jit_dyn_smem + fa.sharedSizeBytes + 1024);
+                    static const unsigned kConfigKb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};   // sm_100 carve-outs
+                    size_t cfg = 228;
+                    for (unsigned kb : kConfigKb) if (size_t(kb) * 1024 >= need) { cfg = kb; break; }
+                    pct = int(std::min<size_t>(100, (cfg * 1024 * 100 + 233471) / 233472));   // rounded up: never below the configuration that holds the blocks
+                }
+                if (pct >= 0 && cudaFuncSetAttribute(reinterpret_cast<const void*>(kern), cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess)
+                    cudaGetLastError();
+            } else cudaGetLastError();
         }
         if (h->jit_ncol || h->jit_nrow) {
             CU_TRY(h, cudaLibraryGetKernel(&g.jit_pre_x, g.libs[0], kJitPreXName));

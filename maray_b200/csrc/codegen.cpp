@@ -381,7 +381,12 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
     Emitter em_pre = em;                       // prologue kernels compute hoisted values, never load them
     if (hoist) { em.load_kind = &load_kind; em.table_index = &table_index; }
 
-    const uint32_t block = opt.block ? ((opt.block + 31) / 32) * 32 : 256;
+    uint32_t block = opt.block ? ((opt.block + 31) / 32) * 32 : 256;
+    uint32_t min_blocks_per_sm = opt.min_blocks_per_sm;
+    if (opt.auto_shape && em.inline_trans && !segmented && !hoist && order.size() >= kOneBlockPerSmValues) {
+        block = 640;
+        min_blocks_per_sm = 1;
+    }
     const bool use_batches = !em.inline_trans;
     const bool scratch = use_batches && opt.scratch_batches;
     em.scratch_batches = scratch;
@@ -398,9 +403,9 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
 
     char buf[320];
     auto kernel_head = [&](std::string& out, const char* extra_args) {
-        if (opt.min_blocks_per_sm)
+        if (min_blocks_per_sm)
             std::snprintf(buf, sizeof buf, "extern \"C\" __global__ void __launch_bounds__(%u, %u) %s(const MrParams p%s) {\n",
-                          block, opt.min_blocks_per_sm, kJitKernelName, extra_args);
+                          block, min_blocks_per_sm, kJitKernelName, extra_args);
         else
             std::snprintf(buf, sizeof buf, "extern \"C\" __global__ void __launch_bounds__(%u) %s(const MrParams p%s) {\n",
                           block, kJitKernelName, extra_args);

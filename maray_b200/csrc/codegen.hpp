@@ -18,6 +18,15 @@ struct CodegenOptions {
     // sin/exp/ln are inlined below this many transcendental values, called out-of-line above it
     // (their inlined bodies dominate code size and compile time in transcendental-heavy scenes).
     uint32_t inline_transcendentals_below = kOutOfLineTranscendentals;
+    // Launch shape chosen from the program (see `block`, `min_blocks_per_sm`): a LARGE straight-line program -- one
+    // kernel, sin/exp/ln inlined, at least kOneBlockPerSmValues values: hundreds of KB of code that no warp re-uses --
+    // runs as ONE 640-thread block per SM (96 registers, 20 warps).  Warps that start together stay within the
+    // instruction caches' reach of each other and share fetches; separately scheduled small blocks each stream the
+    // code on their own.  Measured, chess_4k (profiles/r02c_variants_chess4k_launch_shape.jsonl): 256 x 2 3.86 ms,
+    // 640 x 1 3.48 ms -- and 128 x 5, the same registers and warps in five blocks, 4.75 ms.  Sizes that are not a
+    // multiple of 128 (uneven warps per scheduler) lose 8 %.  Everything else keeps 256 x 2.  false = `block` and
+    // `min_blocks_per_sm` as given (set by MARAY_JIT_BLOCK / MARAY_JIT_MIN_BLOCKS).
+    bool auto_shape = true;
     // Threads per block of the generated kernel (a multiple of 32; one pixel per thread).
     uint32_t block = 256;
     // __launch_bounds__ second argument: resident blocks per SM the register allocation must allow
@@ -75,6 +84,7 @@ struct CodegenInfo {
 
 // Names of the generated kernels (extern "C").
 extern const char* const kJitKernelName;
+constexpr uint32_t kOneBlockPerSmValues = 4096;   // CodegenOptions::auto_shape
 constexpr const char* kJitPreXName = "maray_pre_x";
 constexpr const char* kJitPreYName = "maray_pre_y";
 

@@ -316,6 +316,8 @@ def by_name(name: str) -> Tuple[bytes, List[np.ndarray], Tuple[int, int]]:
         return chess_4k(), [], (3840, 2160)
     if name == "textured":
         return textured(), synthetic_textures(), (3840, 2160)
+    if name == "chess_dsl":
+        return chess_dsl(3840, 2160), [], (3840, 2160)
     if name == "deep":
         # MARAY_DEEP_VALUES shrinks the program for quick experiments (the benchmark config is 100 000)
         return deep(n_values=int(os.environ.get("MARAY_DEEP_VALUES", "100000"))), [], (8192, 8192)
