@@ -39,6 +39,9 @@ struct Emitter {
     const Program& P;
     bool inline_trans;
     const std::vector<int32_t>* bank_index;   // value id -> index in the __constant__ table, or -1
+    // Use-ordered table (CodegenOptions::constants_in_use_order): every constant OPERAND gets the next entry, so
+    // the constants of neighbouring statements are neighbours in the bank.
+    std::vector<uint64_t>* use_bank = nullptr;
     // In the per-pixel kernel a hoisted value is a load from its table: 1 = column table, 2 = row table.
     const std::vector<uint8_t>* load_kind = nullptr;
     const std::vector<uint32_t>* table_index = nullptr;
@@ -70,7 +73,14 @@ struct Emitter {
     void operand(std::string& s, uint32_t id) const {
         const Node& n = P.nodes[id];
         if (n.op == OP_CONST) {
-            if (bank_index && (*bank_index)[id] >= 0) {
+            if (bank_index && (*bank_index)[id] >= 0 && use_bank && use_bank->size() < 8000) {
+                char kb[24];
+                uint64_t bits;
+                std::memcpy(&bits, &n.k, 8);
+                std::snprintf(kb, sizeof kb, "MRK(%zu)", use_bank->size());
+                use_bank->push_back(bits);
+                s += kb;
+            } else if (bank_index && (*bank_index)[id] >= 0 && !use_bank) {
                 char kb[24];
                 std::snprintf(kb, sizeof kb, "MRK(%d)", (*bank_index)[id]);
                 s += kb;
@@ -358,6 +368,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         return t;
     };
     const Bank whole_bank = make_bank(0, 0, true);
+    const bool use_order = opt.constants_in_bank && opt.constants_in_use_order;
 
     Emitter em{prog, n_trans < opt.inline_transcendentals_below, opt.constants_in_bank ? &whole_bank.index : nullptr};
     const std::vector<uint8_t> booleans = opt.boolean_logic ? find_booleans(prog) : std::vector<uint8_t>();
@@ -528,7 +539,9 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
             std::string unit;
             unit.reserve((seg_hi(s) - seg_lo(s)) * 56 + prelude.size() + 4096);
             unit += prelude;
-            unit += bank_text(bk);
+            Bank used;                                   // the use-ordered table is known once the body is written
+            const size_t bank_pos = unit.size();
+            if (use_order) e.use_bank = &used.bits; else unit += bank_text(bk);
             std::snprintf(buf, sizeof buf, "// segment %u of %u\n", s, n_seg);
             unit += buf;
             kernel_head(unit, ", double* __restrict__ F, const unsigned long long FS");
@@ -545,6 +558,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
             emit_range(unit, e, seg_lo(s), seg_hi(s), gref, "if (active) ");
             if (last) store_call(unit, slot, gref, e, &in_scope);
             else unit += "}\n";
+            if (use_order) unit.insert(bank_pos, bank_text(used));
             modules.push_back(std::move(unit));
         }
     } else {
@@ -552,7 +566,10 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         std::string src;
         src.reserve(order.size() * 40 + 8192);
         src += prelude;
-        src += bank_text(whole_bank);
+        Bank used;
+        const size_t bank_pos = src.size();
+        const bool use_order_here = use_order && !segmented && !hoist;
+        if (use_order_here) em.use_bank = &used.bits; else src += bank_text(whole_bank);
         auto lref = [](int32_t f) { return "F[" + std::to_string(f) + "]"; };
         if (segmented) {
             for (uint32_t s = 0; s < n_seg; s++) {
@@ -591,6 +608,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
             emit_range(src, em, 0, order.size(), lref, "");
         }
         store_call(src, slot, lref, em, nullptr);
+        if (use_order_here) { src.insert(bank_pos, bank_text(used)); em.use_bank = nullptr; }
 
         // Prologue kernels: one thread per column / per row evaluates the x-only / y-only sub-program and
         // stores its frontier values (k-major, so the per-pixel kernel's column loads are coalesced and

@@ -40,6 +40,10 @@ struct CodegenOptions {
     // Scene constants live in a __constant__ table and are read as c[bank][offset] operands of the
     // FP64 instructions instead of being materialised with two 32-bit moves each.
     bool constants_in_bank = true;
+    // The table holds one entry per constant OPERAND, in statement order, instead of one per distinct constant:
+    // sm_100 has no constant-bank operands for FP64 instructions (every constant is an LDCU into a uniform register
+    // first), and neighbours in the table can share one 128-bit load.
+    bool constants_in_use_order = false;
     // Evaluate x-only / y-only values once per column / row in prologue kernels and load them in the
     // per-pixel kernel (the GPU form of the reference's row cache).  OFF by default: measured on
     // B200 it LOSES (chess_4k 9.95 ms vs 7.77 ms, sdf 0.225 vs 0.184 ms) -- the 417 table loads per
