@@ -46,6 +46,7 @@ struct HostTexture { uint32_t w, h; std::vector<uint8_t> rgb; };
 
 struct Gpu {
     int device = 0;
+    int sms = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // pipelined host renders (render_frame_pipelined): one stream + event per row chunk, one copy stream
@@ -508,6 +509,7 @@ int jit_build(const Program& prog, JitBuild* jb, bool cached_only, const std::at
     if (const char* e = std::getenv("MARAY_JIT_INLINE_TRANS_BELOW")) copt.inline_transcendentals_below = uint32_t(std::strtoul(e, nullptr, 10));
     if (const char* e = std::getenv("MARAY_JIT_SYNC_EVERY")) copt.sync_every = uint32_t(std::strtoul(e, nullptr, 10));
     if (const char* e = std::getenv("MARAY_JIT_CONST_BANK")) copt.constants_in_bank = std::strtoul(e, nullptr, 10) != 0;
+    if (const char* e = std::getenv("MARAY_JIT_PERSISTENT")) copt.persistent = std::strtoul(e, nullptr, 10) != 0;
     if (const char* e = std::getenv("MARAY_JIT_CONST_ORDER")) copt.constants_in_use_order = std::strtoul(e, nullptr, 10) != 0;
     if (const char* e = std::getenv("MARAY_JIT_HOIST")) copt.hoist = std::strtoul(e, nullptr, 10) != 0;
     if (const char* e = std::getenv("MARAY_JIT_BOOLEAN")) copt.boolean_logic = std::strtoul(e, nullptr, 10) != 0;
@@ -707,6 +709,8 @@ int launch_band(maray_cuda* h, Gpu& g, uint32_t w, uint32_t p0, uint32_t n, uint
         if (!h->jit_chain) {
             void* args[] = {&p};
             unsigned grid = (n + h->jit_block - 1) / h->jit_block;
+            if (h->jit.info.persistent_blocks_per_sm)     // the kernel walks the band's blocks itself
+                grid = std::min(grid, unsigned(g.sms) * h->jit.info.persistent_blocks_per_sm);
             CU_TRY(h, cudaLaunchKernel(reinterpret_cast<const void*>(g.jit_kernels[0]), dim3(grid), dim3(h->jit_block), args, h->jit_dyn_smem, stream));
             if (g.hoist_done && (h->jit_ncol || h->jit_nrow)) CU_TRY(h, cudaEventRecord(g.hoist_done, stream));
         } else {
@@ -1041,6 +1045,7 @@ int maray_cuda_create(int n_gpus, const int* device_ids, maray_cuda_t** out) {
             Gpu& g = h->gpus[i];
             CU_TRY(hp, cudaSetDevice(g.device));
             CU_TRY(hp, cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+            if (cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, g.device) != cudaSuccess || g.sms <= 0) { g.sms = 148; cudaGetLastError(); }
             CU_TRY(hp, cudaEventCreate(&g.ev0));
             CU_TRY(hp, cudaEventCreate(&g.ev1));
             CU_TRY(hp, cudaMalloc(&g.d_sink, 256));

@@ -398,6 +398,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         block = 640;
         min_blocks_per_sm = 1;
     }
+    const bool persistent = opt.persistent && !segmented && !hoist && min_blocks_per_sm > 0;
     const bool use_batches = !em.inline_trans;
     const bool scratch = use_batches && opt.scratch_batches;
     em.scratch_batches = scratch;
@@ -422,6 +423,10 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
                           block, kJitKernelName, extra_args);
         out += buf;
         out += "  __shared__ unsigned int stage[3 * " + std::to_string(block) + " / 4];\n  (void)stage;\n";
+        if (persistent) {   // one resident block walks the band: blocks blockIdx.x, blockIdx.x + gridDim.x, ...
+            out += "  for (unsigned int blk = blockIdx.x; blk * blockDim.x < p.n; blk += gridDim.x) {\n";
+            out += "  const unsigned int j = blk * blockDim.x + threadIdx.x;\n";
+        } else
         out += "  const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;\n";
         out += "  const bool active = j < p.n;\n";
         out += "  const unsigned int pix = p.p0 + (active ? j : 0u);\n";   // idle lanes redo pixel p0
@@ -432,14 +437,14 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
     };
     auto store_call = [&](std::string& out, const std::vector<int32_t>& slot, const std::function<std::string(int32_t)>& frame_ref,
                           const Emitter& e, const std::vector<uint8_t>* in_scope) {
-        out += "  mr_store_block(p, stage, ";
+        out += persistent ? "  mr_store_block_at(p, stage, " : "  mr_store_block(p, stage, ";
         for (int c = 0; c < 3; c++) {
             uint32_t r = prog.root[c];
             if (slot[r] >= 0 && !(in_scope && (*in_scope)[r])) out += frame_ref(slot[r]);
             else e.operand(out, r);
             out += ", ";
         }
-        out += "active, j);\n}\n";
+        out += persistent ? "active, j, blk * blockDim.x);\n  __syncthreads();\n  }\n}\n" : "active, j);\n}\n";
     };
 
     std::vector<std::string> modules;
@@ -644,6 +649,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         info->frame_slots = segmented ? frame_slots : 0;
         info->transcendentals_inlined = em.inline_trans;
         info->block = block;
+        info->persistent_blocks_per_sm = persistent ? min_blocks_per_sm : 0;
         info->n_col = hoist ? uint32_t(prog.col_values.size()) : 0;
         info->n_row = hoist ? uint32_t(prog.row_values.size()) : 0;
         info->dynamic_smem_bytes = scratch ? 2 * kScratchRows * block * uint32_t(sizeof(double)) : 0;   // argument rows + result rows

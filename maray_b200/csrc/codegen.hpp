@@ -27,6 +27,9 @@ struct CodegenOptions {
     // multiple of 128 (uneven warps per scheduler) lose 8 %.  Everything else keeps 256 x 2.  false = `block` and
     // `min_blocks_per_sm` as given (set by MARAY_JIT_BLOCK / MARAY_JIT_MIN_BLOCKS).
     bool auto_shape = true;
+    // The kernel of an unsegmented program loops over the blocks of its band (grid = resident blocks) instead of
+    // being launched once per block: no block hand-over on the SM between two blocks (MARAY_JIT_PERSISTENT).
+    bool persistent = false;
     // Threads per block of the generated kernel (a multiple of 32; one pixel per thread).
     uint32_t block = 256;
     // __launch_bounds__ second argument: resident blocks per SM the register allocation must allow
@@ -82,6 +85,7 @@ struct CodegenInfo {
     uint32_t frame_slots = 0;       // doubles per pixel of the frame that carries values across cuts (0 when not segmented)
     bool transcendentals_inlined = true;
     uint32_t block = 256;           // threads per block the kernel must be launched with
+    uint32_t persistent_blocks_per_sm = 0;   // != 0: the kernel loops over blocks; launch at most SMs x this many
     uint32_t n_col = 0, n_row = 0;  // doubles per column / per row in the hoisting tables (0 = no prologue)
     uint32_t dynamic_smem_bytes = 0; // dynamic shared memory the kernel must be launched with (batch scratch)
 };

@@ -92,8 +92,8 @@ struct MrParams {
 
 // Packs one pixel into the block's staging tile and writes the tile with coalesced 16-byte
 // stores (768 B per 256 pixels).  Every thread of the block must call this.
-__device__ __forceinline__ void mr_store_block(const MrParams& p, unsigned int* stage, double r, double g, double b,
-                                               bool active, unsigned int j) {
+__device__ __forceinline__ void mr_store_block_at(const MrParams& p, unsigned int* stage, double r, double g, double b,
+                                                  bool active, unsigned int j, const unsigned int first) {
     const unsigned int tid = threadIdx.x;
     unsigned char* sb = reinterpret_cast<unsigned char*>(stage);
     sb[3u * tid + 0u] = (unsigned char)mr_as_u8(r);
@@ -105,7 +105,6 @@ __device__ __forceinline__ void mr_store_block(const MrParams& p, unsigned int* 
         p.f64_out[2u * (size_t)p.f64_plane + j] = b;
     }
     __syncthreads();
-    const unsigned int first = blockIdx.x * blockDim.x;
     const unsigned int valid = (p.n - first < blockDim.x) ? (p.n - first) : blockDim.x;
     unsigned char* dst = p.out + 3u * (size_t)first;
     if (p.out_aligned && valid == blockDim.x && (blockDim.x & 15u) == 0u) {
@@ -114,6 +113,11 @@ __device__ __forceinline__ void mr_store_block(const MrParams& p, unsigned int* 
     } else {
         for (unsigned int i = tid; i < 3u * valid; i += blockDim.x) dst[i] = sb[i];
     }
+}
+
+__device__ __forceinline__ void mr_store_block(const MrParams& p, unsigned int* stage, double r, double g, double b,
+                                               bool active, unsigned int j) {
+    mr_store_block_at(p, stage, r, g, b, active, j, blockIdx.x * blockDim.x);
 }
 
 #endif  // MARAY_DEVICE_SEM_CUH
