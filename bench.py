@@ -8,7 +8,9 @@
 A "step" renders one whole frame of the workload.  One process per GPU: rank r renders its row band
 on its own GPU through the C ABI (maray_cuda_render_band); at N > 1 the band kernels store straight into
 rank 0's frame over NVLink (CUDA IPC mapping) and a one-element reduce to rank 0 signals completion -- the
-path's only exchange.  Rank 0 prints ONE JSON line.
+path's only exchange (--completion counters: the C ABI's own signal instead, one 4-byte atomic per rank into a
+counter behind that frame and a bounded wait on rank 0's stream; a few microseconds in the common case but with
+sub-millisecond outliers at N = 2, so the reduce stays the default).  Rank 0 prints ONE JSON line.
 
   value     whole-frame Mpixel/s of the headline workload (chess_4k), frame left in HBM on rank 0
             (device-timed, max over ranks)
@@ -70,6 +72,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cpu-jit-standin", action="store_true",
                     help="skip the second CPU baseline (generated straight-line program built with g++, oracle/jit_standin.py)")
+    ap.add_argument("--completion", default="nccl", choices=["nccl", "counters"],
+                    help="N > 1: how rank 0 learns that every band has landed: a one-element NCCL reduce to rank 0, or the "
+                         "C ABI's completion counters behind the shared frame (maray_cuda_band_signal / _wait)")
     ap.add_argument("--size", default=None, help="WxH override of the workload's frame size (experiments only)")
     ap.add_argument("--configs", default="all",
                     help="sub-records for the other BASELINE configs: all | none | comma list (chess_1k,sdf,textured,deep)")
@@ -316,7 +321,8 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
 
     value    whole-frame Mpixel/s, frame left in rank 0's HBM.  N = 1: the band IS the frame.  N > 1: every rank's
              band kernel stores straight into rank 0's frame over NVLink (CUDA IPC mapping); the step ends with a
-             one-element reduce to rank 0, the signal that every band has landed -- the path's only exchange.
+             one-element reduce to rank 0, the signal that every band has landed -- the path's only exchange
+             (--completion counters: maray_cuda_band_signal / maray_cuda_band_wait instead).
     e2e      N = 1: the C ABI's maray_cuda_render into a PAGEABLE host image (what a Rust Vec<u8>/RgbImage is).
              N > 1: every rank renders its band locally and copies it over its own PCIe link into one pinned host
              frame shared by the ranks (POSIX shared memory), then the same completion signal.
@@ -372,10 +378,27 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
             frame_ptr = r.frame_import(bytes(hb.cpu().numpy().tobytes()))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
+    step_no = [0]
+    debug_ev = [] if os.environ.get("MARAY_BENCH_DEBUG") else None
+
+    def band_done():
+        """rank 0 learns that every band has landed in its frame"""
+        if args.completion == "nccl":
+            dist.reduce(flag, dst=0)
+            return
+        step_no[0] += 1
+        r.band_signal(frame_ptr, w, h, rank, step_no[0], stream.cuda_stream)
+        if rank == 0:
+            if debug_ev is not None:
+                debug_ev.append(torch.cuda.Event(enable_timing=True)); debug_ev[-1].record(stream)
+            r.band_wait(frame_ptr, w, h, world, step_no[0], stream.cuda_stream)
+            if debug_ev is not None:
+                debug_ev.append(torch.cuda.Event(enable_timing=True)); debug_ev[-1].record(stream)
+
     def step_device():
         r.render_band(w, h, y0, y1, frame_ptr + y0 * w * 3, stream.cuda_stream)
         if world > 1:
-            dist.reduce(flag, dst=0)             # rank 0 learns that every band has landed in its frame
+            band_done()
 
     peak_nofma, peak_fma = r.fp64_peak(0)        # roofline denominator of this GPU, before the timed region
 
@@ -396,7 +419,7 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         r.render_band(w, h, y0, y1, frame_ptr + y0 * w * 3, stream.cuda_stream)
         kev[i][1].record(stream)
         if world > 1:
-            dist.reduce(flag, dst=0)
+            band_done()
         ev[i][1].record(stream)
         flush.zero_()            # L2 flush between steps, outside the event pairs
         if world > 1:
@@ -406,6 +429,12 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
     clocks = sampler.stop() if (rank == 0 and full) else None
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / steps
+    if os.environ.get("MARAY_BENCH_DEBUG"):
+        print(f"[bench debug] {name} rank {rank}: step {total_ms / steps:.4f} ms, band kernel {kernel_ms:.4f} ms, "
+              f"per step {[round(a.elapsed_time(b), 3) for a, b in ev][:6]}", file=sys.stderr, flush=True)
+        if debug_ev:
+            waits = [round(debug_ev[k].elapsed_time(debug_ev[k + 1]), 3) for k in range(0, len(debug_ev) - 1, 2)]
+            print(f"[bench debug] {name} rank {rank}: band_wait kernel ms {waits[-steps:][:12]}", file=sys.stderr, flush=True)
     t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -542,7 +571,9 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
             "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
             "config": {"workload": name, "width": w, "height": h, "backend": args.backend,
                        "parallelism": (f"row bands x{world}: band kernels store into rank 0's frame over NVLink (CUDA IPC), "
-                                       "one 4-byte reduce to rank 0 per step signals completion") if world > 1 else "1 GPU",
+                                       + ("one 4-byte store per rank into a completion counter behind that frame, rank 0 waits for the counters"
+                                          if args.completion == "counters" else "one 4-byte reduce to rank 0 per step signals completion"))
+                                      if world > 1 else "1 GPU",
                        "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
                        "dag_values": stats["dag_nodes"], "fp64_ops_per_pixel": ops_px},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": w * h * 3,

@@ -164,6 +164,17 @@ int maray_cuda_render_band(maray_cuda_t* h, uint32_t w, uint32_t hgt, uint32_t y
 #define MARAY_IPC_HANDLE_BYTES 64
 int maray_cuda_frame_export(maray_cuda_t* h, uint32_t w, uint32_t hgt, void* handle64, void** d_frame);
 int maray_cuda_frame_import(maray_cuda_t* h, const void* handle64, void** d_frame);
+/* The completion signal of that arrangement -- its only exchange, and not a collective: 64 counters live behind the
+ * exported frame (same allocation, so every importer has them mapped).  maray_cuda_band_signal, enqueued on `stream`
+ * after the band kernel, writes `value` into counter `rank` (one 4-byte atomic exchange over NVLink, system-scope
+ * release: whoever sees the counter sees the band; each counter has a 128-byte line of its own).  maray_cuda_band_wait, on the exporting process, enqueues a wait until counters
+ * [0, n_ranks) have all reached `value` (counters only grow: pass the step number).  The wait is bounded (~2 s); a
+ * time-out is reported by the next maray_cuda_copy_to_host on that handle.  Pass the pointer frame_export /
+ * frame_import returned, and the same w, hgt.  The poll is an atomic too: polled with loads, B200 shows a peer's
+ * store tens of milliseconds late.  For hosts without a collective library; bench.py keeps NCCL's
+ * one-element reduce as its default signal (measured next to each other: `bench.py --completion counters`). */
+int maray_cuda_band_signal(maray_cuda_t* h, void* d_frame, uint32_t w, uint32_t hgt, uint32_t rank, uint32_t value, void* stream);
+int maray_cuda_band_wait(maray_cuda_t* h, void* d_frame, uint32_t w, uint32_t hgt, uint32_t n_ranks, uint32_t value, void* stream);
 /* Synchronous device -> host copy on the handle's first GPU (reads back a frame held by maray_cuda_frame_export /
  * maray_cuda_render_device without the caller needing a CUDA binding of its own). */
 int maray_cuda_copy_to_host(maray_cuda_t* h, const void* d_src, void* host_dst, size_t bytes);

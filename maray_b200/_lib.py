@@ -61,6 +61,8 @@ SYMBOLS = [
     ("maray_cuda_render_band", ctypes.c_int, [_P, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _P, _P]),
     ("maray_cuda_frame_export", ctypes.c_int, [_P, ctypes.c_uint32, ctypes.c_uint32, _P, ctypes.POINTER(_P)]),
     ("maray_cuda_frame_import", ctypes.c_int, [_P, _P, ctypes.POINTER(_P)]),
+    ("maray_cuda_band_signal", ctypes.c_int, [_P, _P] + [ctypes.c_uint32] * 4 + [_P]),
+    ("maray_cuda_band_wait", ctypes.c_int, [_P, _P] + [ctypes.c_uint32] * 4 + [_P]),
     ("maray_cuda_copy_to_host", ctypes.c_int, [_P, _P, _P, ctypes.c_size_t]),
     ("maray_cuda_render_window_f64", ctypes.c_int, [_P] + [ctypes.c_uint32] * 6 + [_P, _P]),
     ("maray_cuda_get_stats", ctypes.c_int, [_P, ctypes.POINTER(Stats)]),

@@ -211,6 +211,18 @@ int upload_textures(maray_cuda* h) {
     return MARAY_OK;
 }
 
+// Completion counters of a frame shared between band processes: one 32-bit counter per rank, in the same allocation
+// as the frame (the importers have it mapped already), behind the pixels.
+constexpr uint32_t kBandCounters = 64;
+constexpr uint32_t kBandCounterStride = 32;    // 32-bit words between two counters: one 128-byte line each
+// bit 0: signal by atomic exchange instead of a release store; bits 1-2: poll by atomic add of 0 (1) / volatile load (2)
+// instead of an acquire load.  Default 3, both atomic -- performed at the counter's home L2.  Measured at N = 2 (GPU call
+// 51): polled with LOADS (acquire.sys or volatile; LDG.E.STRONG.SYS + CCTL.IVALL in the SASS) the exporting GPU sees a
+// peer's store 1-50 ms late, with the atomic poll in 6-8 us.
+inline int band_signal_mode() { const char* e = std::getenv("MARAY_BAND_SIGNAL_MODE"); return e ? int(std::strtol(e, nullptr, 10)) : 3; }
+inline size_t band_counters_offset(uint32_t w, uint32_t hgt) { return (size_t(w) * hgt * 3 + 255) & ~size_t(255); }
+inline unsigned int* band_timeout_word(Gpu& g) { return reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(g.d_sink) + 128); }
+
 int ensure_out(maray_cuda* h, Gpu& g, size_t bytes) {
     if (g.out_cap >= bytes) return MARAY_OK;
     CU_TRY(h, cudaSetDevice(g.device));
@@ -1049,6 +1061,7 @@ int maray_cuda_create(int n_gpus, const int* device_ids, maray_cuda_t** out) {
             CU_TRY(hp, cudaEventCreate(&g.ev0));
             CU_TRY(hp, cudaEventCreate(&g.ev1));
             CU_TRY(hp, cudaMalloc(&g.d_sink, 256));
+            CU_TRY(hp, cudaMemset(g.d_sink, 0, 256));
             if (i > 0) {
                 int can = 0;
                 cudaDeviceCanAccessPeer(&can, g.device, h->gpus[0].device);
@@ -1243,8 +1256,9 @@ int maray_cuda_frame_export(maray_cuda_t* h, uint32_t w, uint32_t hgt, void* han
     static_assert(sizeof(cudaIpcMemHandle_t) == MARAY_IPC_HANDLE_BYTES, "CUDA IPC handle size");
     Gpu& g = h->gpus[0];
     CU_TRY(h, cudaSetDevice(g.device));
-    rc = ensure_out(h, g, size_t(w) * hgt * 3);
+    rc = ensure_out(h, g, band_counters_offset(w, hgt) + kBandCounters * kBandCounterStride * sizeof(uint32_t));   // frame + completion counters
     if (rc) return rc;
+    CU_TRY(h, cudaMemset(g.d_out + band_counters_offset(w, hgt), 0, kBandCounters * kBandCounterStride * sizeof(uint32_t)));
     cudaIpcMemHandle_t hd;
     CU_TRY(h, cudaIpcGetMemHandle(&hd, g.d_out));
     std::memcpy(handle64, &hd, sizeof hd);
@@ -1265,11 +1279,40 @@ int maray_cuda_frame_import(maray_cuda_t* h, const void* handle64, void** d_fram
     return MARAY_OK;
 }
 
+int maray_cuda_band_signal(maray_cuda_t* h, void* d_frame, uint32_t w, uint32_t hgt, uint32_t rank, uint32_t value, void* stream) {
+    if (!h || !d_frame || rank >= kBandCounters) return fail(h, MARAY_E_INVALID, "maray_cuda_band_signal: bad argument");
+    if (h->gpus.empty()) return fail(h, MARAY_E_CUDA, "host-only handle");
+    CU_TRY(h, cudaSetDevice(h->gpus[0].device));
+    auto* counters = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_frame) + band_counters_offset(w, hgt));
+    CU_TRY(h, launch_band_signal(counters + size_t(rank) * kBandCounterStride, value, static_cast<cudaStream_t>(stream), band_signal_mode()));
+    return MARAY_OK;
+}
+
+int maray_cuda_band_wait(maray_cuda_t* h, void* d_frame, uint32_t w, uint32_t hgt, uint32_t n_ranks, uint32_t value, void* stream) {
+    if (!h || !d_frame || n_ranks == 0 || n_ranks > kBandCounters) return fail(h, MARAY_E_INVALID, "maray_cuda_band_wait: bad argument");
+    if (h->gpus.empty()) return fail(h, MARAY_E_CUDA, "host-only handle");
+    Gpu& g = h->gpus[0];
+    CU_TRY(h, cudaSetDevice(g.device));
+    auto* counters = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_frame) + band_counters_offset(w, hgt));
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device) != cudaSuccess || khz <= 0) { khz = 2000000; cudaGetLastError(); }
+    CU_TRY(h, launch_band_wait(counters, kBandCounterStride, n_ranks, value, band_timeout_word(g), 2000ll * khz,
+                               static_cast<cudaStream_t>(stream), band_signal_mode()));   // ~2 s
+    return MARAY_OK;
+}
+
 int maray_cuda_copy_to_host(maray_cuda_t* h, const void* d_src, void* host_dst, size_t bytes) {
     if (!h || !d_src || !host_dst) return fail(h, MARAY_E_INVALID, "maray_cuda_copy_to_host: null argument");
     if (h->gpus.empty()) return fail(h, MARAY_E_CUDA, "host-only handle");
-    CU_TRY(h, cudaSetDevice(h->gpus[0].device));
+    Gpu& g = h->gpus[0];
+    CU_TRY(h, cudaSetDevice(g.device));
     CU_TRY(h, cudaMemcpy(host_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    uint32_t timed_out = 0;                       // a band wait that gave up: the frame may be incomplete
+    CU_TRY(h, cudaMemcpy(&timed_out, band_timeout_word(g), sizeof timed_out, cudaMemcpyDeviceToHost));
+    if (timed_out) {
+        CU_TRY(h, cudaMemset(band_timeout_word(g), 0, sizeof timed_out));
+        return fail(h, MARAY_E_CUDA, "maray_cuda_band_wait timed out: a band process never signalled");
+    }
     return MARAY_OK;
 }
 

@@ -1,6 +1,7 @@
 // Hand-written sm_100a kernels of the render path:
 //   maray_interp<P>   -- the bytecode interpreter (MARAY_BACKEND_INTERP), P pixels per thread
 //   fp64_issue_rate   -- FP64-pipe issue-rate microbenchmark (the roofline denominator)
+//   band_signal/wait  -- the completion signal of the one-process-per-GPU band render (counters behind the shared frame)
 // The NVRTC back end's kernel is generated at run time (codegen.cpp) from the same device_sem.cuh.
 //
 // Compiled with --fmad=false: the reference never fuses a*b+c.
@@ -426,6 +427,53 @@ __global__ void __launch_bounds__(256) fp64_issue_rate(double* sink, int iters, 
 cudaError_t launch_fp64_issue_rate(bool fma, double* d_sink, int iters, int blocks, cudaStream_t stream) {
     if (fma) fp64_issue_rate<true><<<blocks, 256, 0, stream>>>(d_sink, iters, 1.0000001, 1e-9);
     else fp64_issue_rate<false><<<blocks, 256, 0, stream>>>(d_sink, iters, 1.0000001, 1e-9);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Completion signal between the processes that render row bands into one frame (api.cu: maray_cuda_band_signal /
+// maray_cuda_band_wait).  A band kernel's stores into the frame of GPU 0 travel over NVLink; the kernel boundary
+// orders them before this one 4-byte store, and the store is a system-scope release, so a reader that has seen the
+// counter reach `value` (system-scope acquire) sees the band.  The wait is bounded: after ~2 s of polling it records
+// a time-out and ends, so a lost peer can never hang the GPU.
+__global__ void band_signal(unsigned int* counter, unsigned int value, int mode) {
+    __threadfence_system();
+    if (mode & 1) {   // performed at the home L2 of the counter (the exporting GPU), like every atomic over NVLink
+        unsigned int old;
+        asm volatile("atom.exch.release.sys.global.b32 %0, [%1], %2;" : "=r"(old) : "l"(counter), "r"(value) : "memory");
+        (void)old;
+    } else {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(counter), "r"(value) : "memory");
+    }
+    __threadfence_system();
+}
+
+__global__ void band_wait(unsigned int* counters, unsigned int stride, unsigned int n, unsigned int value, unsigned int* timed_out,
+                          long long max_cycles, int mode) {
+    const unsigned int i = threadIdx.x;
+    if (i >= n) return;
+    unsigned int* c = counters + size_t(i) * stride;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned int seen;
+        if ((mode >> 1) == 1) asm volatile("atom.add.acquire.sys.global.u32 %0, [%1], 0;" : "=r"(seen) : "l"(c) : "memory");
+        else if ((mode >> 1) == 2) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory");
+        else asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory");
+        if (int(seen - value) >= 0) break;               // counters only grow; wrapping compare
+        if (clock64() - t0 > max_cycles) { *timed_out = 1u; break; }
+        __nanosleep(64);
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_band_signal(unsigned int* counter, unsigned int value, cudaStream_t stream, int mode) {
+    band_signal<<<1, 1, 0, stream>>>(counter, value, mode);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_band_wait(unsigned int* counters, unsigned int stride, unsigned int n, unsigned int value, unsigned int* timed_out,
+                             long long max_cycles, cudaStream_t stream, int mode) {
+    band_wait<<<1, ((n + 31) / 32) * 32, 0, stream>>>(counters, stride, n, value, timed_out, max_cycles, mode);
     return cudaGetLastError();
 }
 

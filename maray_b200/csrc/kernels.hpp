@@ -36,4 +36,9 @@ cudaError_t launch_interp(MrTileParams p, const uint64_t* d_code, unsigned int n
 
 cudaError_t launch_fp64_issue_rate(bool fma, double* d_sink, int iters, int blocks, cudaStream_t stream);
 
+// Completion counters of a frame shared by band processes (kernels.cu, "band_signal/wait").
+cudaError_t launch_band_signal(unsigned int* counter, unsigned int value, cudaStream_t stream, int mode);
+cudaError_t launch_band_wait(unsigned int* counters, unsigned int stride, unsigned int n, unsigned int value, unsigned int* timed_out,
+                             long long max_cycles, cudaStream_t stream, int mode);
+
 }  // namespace maray

@@ -245,6 +245,14 @@ class CudaRenderer:
         self._check(self._L.maray_cuda_frame_import(self._h, ctypes.c_char_p(handle), ctypes.byref(p)))
         return p.value
 
+    def band_signal(self, d_frame: int, w: int, h: int, rank: int, value: int, stream: int = 0) -> None:
+        """Counter `rank` behind the shared frame := value, stream-ordered after this process's band kernel."""
+        self._check(self._L.maray_cuda_band_signal(self._h, d_frame, w, h, rank, value, stream))
+
+    def band_wait(self, d_frame: int, w: int, h: int, n_ranks: int, value: int, stream: int = 0) -> None:
+        """Exporting process: `stream` waits until every rank's counter has reached `value` (bounded, ~2 s)."""
+        self._check(self._L.maray_cuda_band_wait(self._h, d_frame, w, h, n_ranks, value, stream))
+
     def copy_to_host(self, d_src: int, out: np.ndarray) -> None:
         self._check(self._L.maray_cuda_copy_to_host(self._h, ctypes.c_void_p(d_src), out.ctypes.data, out.nbytes))
 

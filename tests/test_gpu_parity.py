@@ -15,6 +15,7 @@ from PIL import Image
 
 from maray_b200 import CudaRenderer, RenderMethod, Report, Runtime, Textures, gen_to_image, scenes
 from maray_b200 import expr as E
+from maray_b200.render import MarayCudaError
 from oracle.oracle import OracleScene
 
 from conftest import GOLDEN
@@ -566,6 +567,7 @@ def test_frame_shared_between_processes_over_cuda_ipc(tmp_path):
         want = r.render(w, h)
         handle, frame = r.frame_export(w, h)
         r.render_band(w, h, 0, cut, frame, 0)
+        r.band_signal(frame, w, h, 0, 1, 0)            # completion counters behind the frame: rank 0's band of step 1
         child = (
             "import sys; sys.path.insert(0, %r)\n"
             "import numpy as np\n"
@@ -573,12 +575,23 @@ def test_frame_shared_between_processes_over_cuda_ipc(tmp_path):
             "r = CudaRenderer(gpus=1); r.load(open(%r, 'rb').read()); r.compile('nvrtc')\n"
             "p = r.frame_import(bytes.fromhex(%r))\n"
             "r.render_band(%d, %d, %d, %d, p + %d, 0)\n"
+            "r.band_signal(p, %d, %d, 1, 1, 0)                           # rank 1's band of step 1 has landed\n"
             "probe = np.zeros(1, np.uint8); r.copy_to_host(p, probe)   # default-stream copy: the band kernel is done\n"
-            "r.close()\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(scene_path), handle.hex(), w, h, cut, h, cut * w * 3))
+            "r.close()\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(scene_path), handle.hex(), w, h, cut, h, cut * w * 3, w, h))
         res = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stderr[-2000:]
+        r.band_wait(frame, w, h, 2, 1, 0)              # both counters are at 1: returns at once
         got = np.zeros((h, w, 3), dtype=np.uint8)
         r.copy_to_host(frame, got)
+        assert np.array_equal(got, want)
+        # nobody signals step 2: the wait is bounded, and the next copy reports the time-out
+        import time
+        t0 = time.perf_counter()
+        r.band_wait(frame, w, h, 2, 2, 0)
+        with pytest.raises(MarayCudaError, match="timed out"):
+            r.copy_to_host(frame, got)
+        assert 1.0 < time.perf_counter() - t0 < 10.0
+        r.copy_to_host(frame, got)                     # the flag is cleared: the handle stays usable
     assert np.array_equal(got, want)
 
 
