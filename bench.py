@@ -363,6 +363,7 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
     y0, y1 = bands.band(h, world, rank)
     stream = torch.cuda.current_stream()
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    align = torch.zeros(1, dtype=torch.int32, device=dev)
     if world == 1:
         frame = torch.empty(h * w * 3, dtype=torch.uint8, device=dev)
         frame_ptr = frame.data_ptr()
@@ -423,7 +424,10 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         ev[i][1].record(stream)
         flush.zero_()            # L2 flush between steps, outside the event pairs
         if world > 1:
-            dist.barrier()       # every step starts together on all ranks
+            # every step starts together on all ranks: a stream-ordered all-reduce (the GPUs leave it within
+            # microseconds of each other; dist.barrier() would also block the hosts, and their wake-up skew would
+            # then be charged to the step of whichever rank started first)
+            dist.all_reduce(align)
     barrier()
     sampler.mark_end()
     clocks = sampler.stop() if (rank == 0 and full) else None
