@@ -479,10 +479,15 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         host_band = shm.band_view(y0, y1)                                      # this rank's rows of the shared host frame
         pinned = bool(host_band.is_pinned()) if nbytes else True
 
-        # the band in two halves: the first half travels to the host while the second renders (two halves of a
-        # 13.7-round band are 7 rounds each -- no more rounds than the whole band; finer cuts would add rounds)
+        # the band in two parts: the first travels to the host while the second renders.  The cut lies on a ROUND
+        # boundary of the kernel (stats.jit_round_pixels: what the resident blocks of all SMs cover at once), so the two
+        # parts take no more rounds than the whole band -- half of a 10.95-round band would be 6 rounds, twice
         copy_stream = torch.cuda.Stream(device=dev)
         ym = y0 + (y1 - y0 + 1) // 2
+        rp = int(stats.get("jit_round_pixels") or 0)
+        if args.backend != "interp" and rp and (y1 - y0) * w > 2 * rp:
+            rounds = (y1 - y0) * w / rp
+            ym = y0 + max(1, int((int(rounds) // 2) * rp // w))        # whole rows, just under floor(rounds / 2) rounds
         halves = [(ya, yb) for ya, yb in ((y0, ym), (ym, y1)) if yb > ya]
         half_done = [torch.cuda.Event() for _ in halves]
 

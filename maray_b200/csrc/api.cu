@@ -570,6 +570,8 @@ void fill_jit_stats(maray_cuda* h) {
     h->stats.jit_compile_threads = jb.compile_threads;
     h->stats.jit_cache_hit = jb.cache_hit;
     h->stats.jit_registers = jb.registers;
+    h->stats.jit_block = jb.info.block;
+    h->stats.jit_round_pixels = 0;
     h->stats.jit_cubin_bytes = 0;
     for (const std::vector<char>& c : jb.cubins) h->stats.jit_cubin_bytes += uint32_t(c.size());
 }
@@ -601,13 +603,15 @@ int jit_install(maray_cuda* h, JitBuild&& jb) {
                 // Shared-memory carve-out: no more than the resident blocks use, the rest of the 256 KB is L1.  Left to
                 // itself the driver sizes it for the shared-memory occupancy limit (132 KB for the 33 KB scratch kernels,
                 // whose registers allow two blocks), and the spilled values of a large program then miss in a 121 KB L1.
+                const unsigned regs = std::max(1, fa.numRegs), blk = std::max(1u, h->jit_block);
+                const size_t smem_per_block = h->jit_dyn_smem + fa.sharedSizeBytes + 1024;
+                unsigned blocks = std::min(std::min(65536u / ((regs + 7) / 8 * 8 * blk), 2048u / blk), 32u);
+                blocks = std::max(1u, std::min<unsigned>(blocks, unsigned(233472 / smem_per_block)));      // resident blocks per SM
+                if (&g == &h->gpus[0] && &cubin == &h->jit.cubins[0]) h->stats.jit_round_pixels = uint32_t(g.sms) * blocks * blk;
                 int pct = -1;
                 if (const char* e = std::getenv("MARAY_JIT_CARVEOUT")) pct = int(std::strtol(e, nullptr, 10));   // percent; -1 = computed, -2 = driver's choice
                 if (pct == -1) {
-                    unsigned regs = std::max(1, fa.numRegs), blk = std::max(1u, h->jit_block);
-                    unsigned per_thread = (regs + 7) / 8 * 8;
-                    unsigned blocks = std::max(1u, std::min(std::min(65536u / (per_thread * blk), 2048u / blk), 32u));
-                    size_t need = size_t(blocks) * (h->jit_dyn_smem + fa.sharedSizeBytes + 1024);
+                    const size_t need = size_t(blocks) * smem_per_block;
                     static const unsigned kConfigKb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};   // sm_100 carve-outs
                     size_t cfg = 228;
                     for (unsigned kb : kConfigKb) if (size_t(kb) * 1024 >= need) { cfg = kb; break; }
