@@ -576,6 +576,9 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         traffic = committed_dram_traffic(name, args.backend) if world == 1 else None
         roof["traffic"] = traffic["bytes"] if traffic else None
         roof["traffic_source"] = traffic["source"] if traffic else None
+        if traffic and stats["jit_units"] > 1 and args.backend != "interp":
+            roof["traffic_note"] = (f"DRAM bytes of ONE launch of the chain (a frame is {stats['jit_units']} kernels per frame chunk): "
+                                    "the frame of values that cross the cuts and local-memory spills, see the source file's header")
         rec = {
             "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
             "config": {"workload": name, "width": w, "height": h, "backend": args.backend,
