@@ -527,6 +527,7 @@ int jit_build(const Program& prog, JitBuild* jb, bool cached_only, const std::at
     if (const char* e = std::getenv("MARAY_JIT_BOOLEAN")) copt.boolean_logic = std::strtoul(e, nullptr, 10) != 0;
     if (const char* e = std::getenv("MARAY_JIT_SIGN_OF_SINE")) copt.sign_of_sine = std::strtoul(e, nullptr, 10) != 0;
     if (const char* e = std::getenv("MARAY_JIT_SCRATCH")) copt.scratch_batches = std::strtoul(e, nullptr, 10) != 0;
+    if (const char* e = std::getenv("MARAY_JIT_SCRATCH_TABLES")) copt.scratch_tables = std::strtoul(e, nullptr, 10) != 0;
     if (const char* e = std::getenv("MARAY_JIT_PRIVATE_HELPERS")) copt.private_batch_helpers = std::strtoul(e, nullptr, 10) != 0;
     if (const char* e = std::getenv("MARAY_JIT_BATCH_WIDTH")) copt.batch_width = uint32_t(std::strtoul(e, nullptr, 10));
     if (const char* e = std::getenv("MARAY_JIT_BLOCK")) { copt.block = uint32_t(std::strtoul(e, nullptr, 10)); copt.auto_shape = false; }

@@ -409,6 +409,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         if (private_helpers) prelude += "#define MR_NO_DEFAULT_BATCH_HELPERS 1\n";
         prelude += "#define MR_SCR_STRIDE " + std::to_string(block) + "\n";
         prelude += "#define MR_BATCH_WIDTH " + std::to_string(opt.batch_width == 4 ? 4 : 2) + "\n";
+        if (opt.scratch_tables) prelude += "#define MR_SCR_TABLES 1\n";
     }
     prelude += kDeviceSemText;
     prelude += "\n";
@@ -434,6 +435,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         out += "  const unsigned int xi = pix - yi * p.W;\n";
         out += "  const double X = (double)xi;\n  const double Y = (double)yi;\n";   // `x as f64`
         out += "  const MrTexture* __restrict__ T = p.tex;\n  (void)T;\n";
+        if (scratch) out += "  mr_scratch_tables_init();\n";
     };
     auto store_call = [&](std::string& out, const std::vector<int32_t>& slot, const std::function<std::string(int32_t)>& frame_ref,
                           const Emitter& e, const std::vector<uint8_t>* in_scope) {
@@ -653,6 +655,7 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
         info->n_col = hoist ? uint32_t(prog.col_values.size()) : 0;
         info->n_row = hoist ? uint32_t(prog.row_values.size()) : 0;
         info->dynamic_smem_bytes = scratch ? 2 * kScratchRows * block * uint32_t(sizeof(double)) : 0;   // argument rows + result rows
+        if (scratch && opt.scratch_tables) info->dynamic_smem_bytes += 4096;                            // + glibc's exp and log tables
     }
     return modules;
 }

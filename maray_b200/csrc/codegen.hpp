@@ -68,6 +68,9 @@ struct CodegenOptions {
     // shared memory to leaf helpers (device_libm.cuh, "scratch-batched form") instead of through the
     // call ABI's registers.  false = the register-argument x4/x2 helpers.
     bool scratch_batches = true;
+    // The batch helpers read glibc's exp and log tables from shared memory (copied behind the scratch rows once per
+    // block) instead of global memory: two instructions fewer per value and a short-scoreboard latency.
+    bool scratch_tables = true;
     // Independent evaluations per iteration of the batch helpers' loop (2 or 4).  4 since the sine lost its table
     // loads and selects (measured, deep scene at 20 000 values: 13.4 ms against 13.8 with 2; with round 1's sine 4 did
     // not pay: the helper has the ~38 registers its caller leaves).

@@ -49,6 +49,7 @@ MR_DYN_DECL
 #ifndef MR_NO_DEFAULT_BATCH_HELPERS
 MR_BATCH_HELPERS()
 #endif
+MR_PLAIN_FN void mr_scratch_tables_init() {}   // the platform's own exp and log bring their own tables
 #endif
 #else
 
@@ -436,6 +437,28 @@ extern __shared__ double mr_dyn_f64[];
 #endif
 #define MR_W MR_BATCH_WIDTH
 #define MR_EACH _Pragma("unroll") for (int i = 0; i < MR_W; i++)
+// MR_SCR_TABLES: glibc's exp and log tables (2 KB each) sit in shared memory behind the 16 scratch rows, copied there
+// once per block by mr_scratch_tables_init().  A lookup is then one LDS.128 at a 32-bit offset instead of a 64-bit
+// address computation (IADD3 + IMAD.X) and an LDG whose latency is the long scoreboard's.
+#ifdef MR_SCR_TABLES
+#define MR_TAB_EXP (reinterpret_cast<const unsigned long long*>(mr_dyn_f64 + 16 * MR_SCR_STRIDE))
+#define MR_TAB_LOG (mr_dyn_f64 + 16 * MR_SCR_STRIDE + 256)
+#define MR_TAB_LD2U(p, a, b) do { const ulonglong2 v2_ = *reinterpret_cast<const ulonglong2*>(p); (a) = v2_.x; (b) = v2_.y; } while (0)
+#define MR_TAB_LD2(p, a, b) do { const double2 v2_ = *reinterpret_cast<const double2*>(p); (a) = v2_.x; (b) = v2_.y; } while (0)
+__device__ __forceinline__ void mr_scratch_tables_init() {
+    for (unsigned int i = threadIdx.x; i < 256u; i += blockDim.x) {
+        reinterpret_cast<unsigned long long*>(mr_dyn_f64 + 16 * MR_SCR_STRIDE)[i] = MRG_EXP_TAB[i];
+        mr_dyn_f64[16 * MR_SCR_STRIDE + 256 + i] = MRG_LOG_TAB[i];
+    }
+    __syncthreads();
+}
+#else
+#define MR_TAB_EXP MRG_EXP_TAB
+#define MR_TAB_LOG MRG_LOG_TAB
+#define MR_TAB_LD2U(p, a, b) MRG_LDG2U(p, a, b)
+#define MR_TAB_LD2(p, a, b) MR_LDG2(p, a, b)
+__device__ __forceinline__ void mr_scratch_tables_init() {}
+#endif
 // The fast paths again, MR_W evaluations at a time and written STEP-MAJOR: every step is applied to
 // all lanes before the next one, so the lanes' dependent DFMA chains are interleaved in program order.
 // (Left to itself the compiler emits one whole chain after the other -- measured: 47 % of the helpers'
@@ -565,7 +588,7 @@ __device__ __forceinline__ void mr_exp_fast_w_f(const double* x, double* out) {
     MR_EACH {
         const unsigned int ki = (unsigned int)mr_lo32(kd0[i]);
         unsigned long long tb, sb;
-        MRG_LDG2U(MRG_EXP_TAB + 2 * (ki & 127u), tb, sb);
+        MR_TAB_LD2U(MR_TAB_EXP + 2 * (ki & 127u), tb, sb);
         sb += (unsigned long long)ki << 45;
         tail[i] = mr_hilo((int)(tb >> 32), (int)(unsigned int)tb);
         scale[i] = mr_hilo((int)(sb >> 32), (int)(unsigned int)sb);
@@ -586,7 +609,7 @@ __device__ __forceinline__ void mr_log_fast_w_f(const double* x, double* out) {
         const int hx = mr_hi32(x[i]);
         const int th = hx - 0x3fe60000;
         z[i] = mr_hilo(hx - (int)((unsigned int)th & 0xfff00000u), mr_lo32(x[i]));
-        MR_LDG2(MRG_LOG_TAB + 2 * ((th >> 13) & 127), invc[i], logc[i]);
+        MR_TAB_LD2(MR_TAB_LOG + 2 * ((th >> 13) & 127), invc[i], logc[i]);
         kd[i] = (double)(th >> 20);
     }
     MR_EACH w[i] = MR_FMA(kd[i], MRG_LOG_K[0], logc[i]);
@@ -626,7 +649,8 @@ MR_DEFINE_FAST_W(log)
             MR_EACH x[i] = s[i * MR_SCR_STRIDE];   /* rows past n: stale but in bounds, results unused */ \
             mr_##fn##_fast_w(x, r);                                                                    \
             MR_EACH s[(8 + i) * MR_SCR_STRIDE] = r[i];                                                 \
-            MR_EACH all_ok &= mr_##fn##_inrange(x[i]) || (i != 0 && k + i >= n);                       \
+            MR_EACH all_ok &= mr_##fn##_inrange(x[i]);   /* rows past n included: a stale row can only */ \
+                                                         /* raise the flag, and mr_*_fix looks at rows < n */ \
         }                                                                                              \
         return all_ok ? 0u : 1u;                                                                       \
     }                                                                                                  \
