@@ -130,3 +130,36 @@ def test_auto_backend_builds_in_the_background(monkeypatch, tmp_path):
         st = r.compile("auto")
         assert st["jit_cache_hit"] == 1 and st["jit_units"] == 1 and r.stats()["jit_active"] == 1
         assert "maray_jit" in r.source()
+
+
+def test_launch_shape_follows_the_program(monkeypatch, chess_bytes):
+    """Large straight-line programs are generated for one 640-thread block per SM (their warps share instruction
+    fetches), small ones and programs with batched sin/exp/ln helpers for 256 x 2; MARAY_JIT_BLOCK /
+    MARAY_JIT_MIN_BLOCKS set the shape by hand.  (MARAY_JIT_SOURCE_ONLY: the text is generated, NVRTC is not run; the
+    stats of a compiled program carry the shape as jit_block / jit_round_pixels, checked on the GPU.)"""
+    import re
+    monkeypatch.setenv("MARAY_JIT_SOURCE_ONLY", "1")
+
+    def shape(scene, **env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with CudaRenderer(gpus=0) as r:
+            r.load(scene)
+            with pytest.raises(Exception):
+                r.compile("nvrtc")
+            src = r.source()
+        for k in env:
+            monkeypatch.delenv(k)
+        return int(re.search(r"__launch_bounds__\((\d+)", src).group(1)), src
+
+    block, src = shape(chess_bytes)
+    assert block == 640 and "__launch_bounds__(640, 1) maray_jit" in src and "for (unsigned int blk" not in src
+    block, src = shape(chess_bytes, MARAY_JIT_BLOCK="256")
+    assert block == 256 and "__launch_bounds__(256, 2) maray_jit" in src
+    block, src = shape(chess_bytes, MARAY_JIT_PERSISTENT="1")
+    assert block == 640 and "for (unsigned int blk = blockIdx.x; blk * blockDim.x < p.n; blk += gridDim.x)" in src
+    assert "mr_store_block_at(" in src
+    block, src = shape(scenes.sdf(64, 48, 6, seed=4))
+    assert block == 256 and "__launch_bounds__(256, 2) maray_jit" in src
+    block, src = shape(scenes.deep(64, 64, n_values=9000, seed=3))          # batched helpers: scratch rows sized for 256 threads
+    assert block == 256 and "#define MR_SCR_STRIDE 256" in src and "mr_scratch_tables_init();" in src

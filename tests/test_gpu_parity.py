@@ -641,7 +641,8 @@ def test_code_generation_knobs_render_the_same_frame(monkeypatch):
         want = r.render(w, h)
     variants = [{"MARAY_JIT_BATCH_WIDTH": "4"}, {"MARAY_JIT_SCRATCH": "0"}, {"MARAY_JIT_CONST_BANK": "0"},
                 {"MARAY_JIT_CHAIN": "0", "MARAY_JIT_SEGMENT_VALUES": "4096"}, {"MARAY_JIT_CHAIN_SEGMENT_VALUES": "2000", "MARAY_JIT_SEGMENT_VALUES": "4096"},
-                {"MARAY_LIBM_EXPLOG": "poly"}, {"MARAY_JIT_BOOLEAN": "0"}, {"MARAY_JIT_LINEINFO": "0"}]
+                {"MARAY_LIBM_EXPLOG": "poly"}, {"MARAY_JIT_BOOLEAN": "0"}, {"MARAY_JIT_LINEINFO": "0"},
+                {"MARAY_JIT_SCRATCH_TABLES": "0"}, {"MARAY_JIT_CONST_ORDER": "1"}, {"MARAY_JIT_CARVEOUT": "-2"}]
     for env in variants:
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -653,3 +654,40 @@ def test_code_generation_knobs_render_the_same_frame(monkeypatch):
             assert np.abs(got.astype(int) - want.astype(int)).max() <= 1, env
         else:
             assert np.array_equal(got, want), env
+
+
+LAUNCH_SHAPE_VARIANTS = [{"MARAY_JIT_BLOCK": "256"}, {"MARAY_JIT_PERSISTENT": "1"}, {"MARAY_JIT_CONST_ORDER": "1"},
+                         {"MARAY_JIT_BLOCK": "1024", "MARAY_JIT_MIN_BLOCKS": "1"},
+                         {"MARAY_JIT_BLOCK": "128", "MARAY_JIT_MIN_BLOCKS": "5", "MARAY_JIT_PERSISTENT": "1"}]
+
+
+def test_launch_shapes_render_the_same_frame(monkeypatch):
+    """A large straight-line program runs as one 640-thread block per SM by default (DESIGN.md 3.1 "launch shape").
+    The frame must not depend on that choice: ragged sizes (the last block is partial, rows straddle blocks), the old
+    256 x 2 shape, hand-set shapes, the persistent form and the use-ordered constant table render the same bytes, and
+    the default form matches the oracle."""
+    scene = scenes.chess_1k()
+    w, h = 1001, 77                       # 77 077 pixels: not a multiple of 640, 256, 1024 or 128
+    with _renderer(scene, "nvrtc") as r:
+        st = r.stats()
+        assert st["jit_block"] == 640 and st["jit_registers"] <= 96 and st["jit_round_pixels"] % 640 == 0
+        want = r.render(w, h)
+        band = np.zeros((20, w, 3), dtype=np.uint8)
+        # a band that starts inside a block of the frame's own partition
+        import torch
+        d = torch.empty(20 * w * 3, dtype=torch.uint8, device="cuda")
+        r.render_band(w, h, 31, 51, d.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        band[:] = d.cpu().numpy().reshape(20, w, 3)
+    assert np.array_equal(band, want[31:51])
+    want_rgb, _ = OracleScene(scene).render_window(0, w, 40, 44, want_f64=True)
+    assert np.array_equal(want[40:44], want_rgb)
+    for env in LAUNCH_SHAPE_VARIANTS:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with _renderer(scene, "nvrtc") as r:
+            assert r.stats()["jit_block"] == int(env.get("MARAY_JIT_BLOCK", 640))
+            got = r.render(w, h)
+        for k in env:
+            monkeypatch.delenv(k)
+        assert np.array_equal(got, want), env
