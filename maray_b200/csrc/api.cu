@@ -85,6 +85,8 @@ struct JitBuild {
     CodegenInfo info;
     unsigned maxreg = 0;
     int libm = MARAY_LIBM_FAST;               // which sin/exp/ln the units are compiled against (maray_cuda_set_libm)
+    uint64_t frame_pixels = 0;                // the scene's declared size (a hint for the launch shape), 0 = unknown
+    uint32_t sms = 148;                       // SMs of the first GPU (148 without one)
     double codegen_ms = 0.0, nvrtc_ms = 0.0;
     uint32_t registers = 0, compile_threads = 0, cache_hit = 0;
     std::string error;
@@ -517,6 +519,8 @@ int jit_build(const Program& prog, JitBuild* jb, bool cached_only, const std::at
     // Exact mode: the routines branch on ranges and read tables -- always out of line (inlined, chess.maray's 256 sines
     // are 5.7 MB of code and 53 s of NVRTC here instead of 1.7 MB / 11 s).
     if (jb->libm == MARAY_LIBM_GLIBC) copt.inline_transcendentals_below = 0;
+    copt.frame_pixels_hint = jb->frame_pixels;
+    copt.sm_count_hint = jb->sms ? jb->sms : 148;
     if (const char* e = std::getenv("MARAY_JIT_SEGMENT_VALUES")) copt.segment_values = uint32_t(std::strtoul(e, nullptr, 10));
     if (const char* e = std::getenv("MARAY_JIT_INLINE_TRANS_BELOW")) copt.inline_transcendentals_below = uint32_t(std::strtoul(e, nullptr, 10));
     if (const char* e = std::getenv("MARAY_JIT_SYNC_EVERY")) copt.sync_every = uint32_t(std::strtoul(e, nullptr, 10));
@@ -1172,7 +1176,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         rc = interp_build_and_install(h);
     } else if (backend == MARAY_BACKEND_NVRTC) {
         JitBuild jb;
-        jb.libm = h->libm;
+        jb.libm = h->libm; jb.frame_pixels = uint64_t(h->scene.size[0]) * h->scene.size[1]; jb.sms = h->gpus.empty() ? 148u : uint32_t(h->gpus[0].sms);
         rc = jit_build(h->prog, &jb, /*cached_only=*/false, nullptr);
         if (rc) { h->jit = std::move(jb); fill_jit_stats(h); return fail(h, rc, h->jit.error); }   // the generated text stays inspectable
         rc = jit_install(h, std::move(jb));
@@ -1181,7 +1185,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
         // ready in milliseconds -- renders while NVRTC works on another thread; renders switch to the generated
         // kernels, between row chunks, as soon as they are built.  Both back ends produce the same bytes.
         JitBuild jb;
-        jb.libm = h->libm;
+        jb.libm = h->libm; jb.frame_pixels = uint64_t(h->scene.size[0]) * h->scene.size[1]; jb.sms = h->gpus.empty() ? 148u : uint32_t(h->gpus[0].sms);
         rc = jit_build(h->prog, &jb, /*cached_only=*/true, nullptr);
         if (rc == MARAY_OK) {
             rc = jit_install(h, std::move(jb));
@@ -1190,7 +1194,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
             if (rc == MARAY_E_UNSUPPORTED) {
                 // the slot file does not fit: compile now, there is nothing to render with meanwhile
                 JitBuild now;
-                now.libm = h->libm;
+                now.libm = h->libm; now.frame_pixels = uint64_t(h->scene.size[0]) * h->scene.size[1]; now.sms = h->gpus.empty() ? 148u : uint32_t(h->gpus[0].sms);
                 rc = jit_build(h->prog, &now, false, nullptr);
                 if (rc) return fail(h, rc, now.error);
                 rc = jit_install(h, std::move(now));
@@ -1198,7 +1202,7 @@ int maray_cuda_compile(maray_cuda_t* h, int backend, maray_cuda_stats* stats) {
                 h->job.reset(new JitJob());
                 JitJob* job = h->job.get();
                 job->prog = h->prog;
-                job->build.libm = h->libm;
+                job->build.libm = h->libm; job->build.frame_pixels = uint64_t(h->scene.size[0]) * h->scene.size[1]; job->build.sms = h->gpus.empty() ? 148u : uint32_t(h->gpus[0].sms);
                 job->th = std::thread([job] {
                     job->rc = jit_build(job->prog, &job->build, false, &job->cancel);
                     job->state = job->rc == MARAY_OK ? 1 : 2;

@@ -397,6 +397,15 @@ std::vector<std::string> generate(const Program& prog, const CodegenOptions& opt
     if (opt.auto_shape && em.inline_trans && !segmented && !hoist && order.size() >= kOneBlockPerSmValues) {
         block = 640;
         min_blocks_per_sm = 1;
+        if (opt.frame_pixels_hint) {
+            static const struct { uint32_t block; double cost; } kShapes[] = {{640, 1.0}, {768, 1.015}, {1024, 1.02}};
+            double best = 0.0;
+            for (const auto& sh : kShapes) {
+                const uint64_t per_round = uint64_t(opt.sm_count_hint ? opt.sm_count_hint : 148) * sh.block;
+                const double t = double((opt.frame_pixels_hint + per_round - 1) / per_round) * sh.block * sh.cost;
+                if (best == 0.0 || t < best) { best = t; block = sh.block; }
+            }
+        }
     }
     const bool persistent = opt.persistent && !segmented && !hoist && min_blocks_per_sm > 0;
     const bool use_batches = !em.inline_trans;

@@ -27,6 +27,12 @@ struct CodegenOptions {
     // multiple of 128 (uneven warps per scheduler) lose 8 %.  Everything else keeps 256 x 2.  false = `block` and
     // `min_blocks_per_sm` as given (set by MARAY_JIT_BLOCK / MARAY_JIT_MIN_BLOCKS).
     bool auto_shape = true;
+    // The scene's declared frame size and the GPU's SM count, when known: a frame of few rounds pays for its last,
+    // partial round of blocks, so among the one-block-per-SM shapes that measured within 2 % of each other on a
+    // large frame (640 threads / 96 registers 1.00, 768 / 80 1.015, 1 024 / 64 1.02) the one whose rounds fit the
+    // frame best is taken: 1 024 x 1 024 pixels are 11.07 rounds of 640 (12 paid) but 6.92 rounds of 1 024.
+    uint64_t frame_pixels_hint = 0;
+    uint32_t sm_count_hint = 148;
     // The kernel of an unsegmented program loops over the blocks of its band (grid = resident blocks) instead of
     // being launched once per block: no block hand-over on the SM between two blocks (MARAY_JIT_PERSISTENT).
     bool persistent = false;

@@ -152,11 +152,14 @@ def test_launch_shape_follows_the_program(monkeypatch, chess_bytes):
             monkeypatch.delenv(k)
         return int(re.search(r"__launch_bounds__\((\d+)", src).group(1)), src
 
+    # the shipped scene declares 1024 x 1024: 6.92 rounds of 1 024-thread blocks on 148 SMs against 11.07 of 640
     block, src = shape(chess_bytes)
-    assert block == 640 and "__launch_bounds__(640, 1) maray_jit" in src and "for (unsigned int blk" not in src
+    assert block == 1024 and "__launch_bounds__(1024, 1) maray_jit" in src and "for (unsigned int blk" not in src
+    block, src = shape(scenes.chess_4k())             # the same program declared at 3840 x 2160: 87.6 rounds of 640
+    assert block == 640 and "__launch_bounds__(640, 1) maray_jit" in src
     block, src = shape(chess_bytes, MARAY_JIT_BLOCK="256")
     assert block == 256 and "__launch_bounds__(256, 2) maray_jit" in src
-    block, src = shape(chess_bytes, MARAY_JIT_PERSISTENT="1")
+    block, src = shape(scenes.chess_4k(), MARAY_JIT_PERSISTENT="1")
     assert block == 640 and "for (unsigned int blk = blockIdx.x; blk * blockDim.x < p.n; blk += gridDim.x)" in src
     assert "mr_store_block_at(" in src
     block, src = shape(scenes.sdf(64, 48, 6, seed=4))
