@@ -88,6 +88,7 @@ public:
         }
         emit(BC_H_END, 0, 0, 0, 0);
         if (B.consts.size() + B.n_uniform > 0xffff) err = "program has more than 65535 constants and row-uniform values";
+        seq_ = nullptr;                      // `seq` is this call's local
     }
 
 private:
