@@ -483,12 +483,8 @@ def measure(name, args, steps, warmup, rank, local_rank, world, dev, full):
         # boundary of the kernel (stats.jit_round_pixels: what the resident blocks of all SMs cover at once), so the two
         # parts take no more rounds than the whole band -- half of a 10.95-round band would be 6 rounds, twice
         copy_stream = torch.cuda.Stream(device=dev)
-        ym = y0 + (y1 - y0 + 1) // 2
-        rp = int(stats.get("jit_round_pixels") or 0)
-        if args.backend != "interp" and rp and (y1 - y0) * w > 2 * rp:
-            rounds = (y1 - y0) * w / rp
-            ym = y0 + max(1, int((int(rounds) // 2) * rp // w))        # whole rows, just under floor(rounds / 2) rounds
-        halves = [(ya, yb) for ya, yb in ((y0, ym), (ym, y1)) if yb > ya]
+        rp = int(stats.get("jit_round_pixels") or 0) if args.backend != "interp" else 0
+        halves = bands.two_parts_on_a_round(y0, y1, w, rp)
         half_done = [torch.cuda.Event() for _ in halves]
 
         def step_e2e():

@@ -31,6 +31,20 @@ def max_band_rows(h: int, n: int) -> int:
     return max(y1 - y0 for y0, y1 in bands(h, n))
 
 
+def two_parts_on_a_round(y0: int, y1: int, w: int, round_pixels: int) -> List[Tuple[int, int]]:
+    """Cuts the band [y0, y1) of a w-wide frame in two so that the first part can travel to the host while the second
+    renders, WITHOUT adding a round of blocks: `round_pixels` (stats["jit_round_pixels"]) is what the resident blocks of
+    all SMs cover at once, a band of r rounds pays for ceil(r), and two halves of a 10.95-round band would pay for 6
+    each.  The cut therefore lies just under floor(r / 2) whole rounds, on a row boundary; bands of two rounds or
+    less (or an unknown round size) are cut in the middle.  Empty parts are dropped."""
+    rows = y1 - y0
+    ym = y0 + (rows + 1) // 2
+    if round_pixels > 0 and rows * w > 2 * round_pixels:
+        half_rounds = (rows * w // round_pixels) // 2
+        ym = y0 + max(1, half_rounds * round_pixels // w)
+    return [(a, b) for a, b in ((y0, ym), (ym, y1)) if b > a]
+
+
 def gather_bands(band_buf, frame, w: int, h: int, rank: int, world: int, group=None) -> None:
     """Gathers every rank's band into `frame` on rank 0.
 

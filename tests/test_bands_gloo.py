@@ -90,3 +90,25 @@ def test_shared_host_frame_gloo(world, h, tmp_path):
     out = str(tmp_path / "frame.npy")
     mp.spawn(_shared_frame_worker, args=(world, _free_port(), w, h, scene, out), nprocs=world, join=True)
     assert np.array_equal(np.load(out), OracleScene(scene).render(w, h))
+
+
+def test_two_parts_on_a_round():
+    """The e2e path of bench.py copies the first part of a band out while the second renders; the cut must not cost
+    a round of blocks."""
+    import math
+    w, rp = 3840, 148 * 640
+    for n in (2, 4, 8):
+        for r in range(n):
+            y0, y1 = bands.band(2160, n, r)
+            parts = bands.two_parts_on_a_round(y0, y1, w, rp)
+            assert len(parts) == 2 and parts[0][0] == y0 and parts[0][1] == parts[1][0] and parts[1][1] == y1
+            whole = math.ceil((y1 - y0) * w / rp)
+            assert sum(math.ceil((b - a) * w / rp) for a, b in parts) == whole          # 44, 22, 11 rounds: none added
+    # small bands and unknown round sizes: the middle; degenerate bands: no empty part
+    assert bands.two_parts_on_a_round(10, 20, 1024, rp) == [(10, 15), (15, 20)]
+    assert bands.two_parts_on_a_round(0, 135, 1920, 0) == [(0, 68), (68, 135)]
+    assert bands.two_parts_on_a_round(5, 6, 64, rp) == [(5, 6)]
+    assert bands.two_parts_on_a_round(5, 5, 64, rp) == []
+    # chain programs (256 x 2 shape) on a tall band
+    parts = bands.two_parts_on_a_round(0, 1024, 8192, 148 * 2 * 256)
+    assert parts[0][1] == 55 * 148 * 2 * 256 // 8192 and parts[1][1] == 1024
